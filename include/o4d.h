@@ -1,0 +1,220 @@
+/*
+ * o4d.h -- C ABI of libo4d.so, the B200 (sm_100a) implementation of the occlusions-4d
+ * encoder / implicit-decoder hot path.
+ *
+ * The reference (basilevh/occlusions-4d) is pure Python: there is no FFI in it to bind.
+ * Each entry point below therefore names the reference *Python* interface it replaces
+ * (file:line under /root/reference); INTEGRATION.md shows the ctypes stub a maintainer
+ * of the reference would add.  The host-side nn.Module mirror lives in
+ * occlusions-4d_b200/o4d/.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all data pointers are DEVICE pointers unless the
+ *     name ends in _host; row-major contiguous fp32 activations with an explicit
+ *     leading dimension (ld*, in elements) where a view can be strided;
+ *   - neighbour / sample indices are int64 at this boundary (the reference hands out
+ *     torch.int64) and int32 inside;
+ *   - no allocation and no host synchronisation inside compute calls: scratch memory
+ *     is caller-owned (query the size with the matching *_workspace_bytes call);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - every function returns 0 on success, <0 for an invalid argument (O4D_E_*), >0 for
+ *     a cudaError_t raised by a launch; o4d_last_error() gives a message for the
+ *     calling thread.  Nothing aborts.
+ *   - re-entrant: no global mutable state besides the per-thread error string.
+ */
+#ifndef O4D_H_
+#define O4D_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define O4D_OK 0
+#define O4D_E_ARG (-1)      /* bad size / null pointer / unsupported combination */
+#define O4D_E_WORKSPACE (-2) /* workspace too small */
+#define O4D_E_UNSUPPORTED (-3)
+
+#define O4D_MAX_K 16        /* largest neighbour count (pt_num_neighbors<=16) */
+#define O4D_MAX_BLOCKS 16   /* largest n_blocks / down_blocks accepted */
+
+const char* o4d_last_error(void);
+/* ABI version of this header; bumped on any signature change. */
+int o4d_abi_version(void);
+/* 1 when the library was built with the tcgen05 (tensor-core) GEMM path. */
+int o4d_has_tcgen05(void);
+
+/* ------------------------------------------------------------------ kNN
+ * Brute-force k nearest neighbours in 3-D, ascending (distance, index), distance =
+ * fp32 ((dx*dx + dy*dy) + dz*dz) without FMA contraction.
+ * Replaces kNN_torch, model/point_transformer_layer.py:76-99 (sqrt_dist = 0, squared
+ * distances, the reference argsorts them) and my_knn_torch, utils/geometry.py:458-503
+ * (sqrt_dist = 1: ordering and returned distances are Euclidean), and the neighbour
+ * search of torch_cluster.knn at model/modules.py:142-146.
+ *   query  (nq, ldq>=3)  xyz in the first three columns
+ *   ref    (m,  ldr>=3)
+ *   idx_out  (nq, k) int64           dist_out (nq, k) fp32 or NULL
+ * Requires 1 <= k <= min(m, O4D_MAX_K). */
+int o4d_knn_f32(const float* query, int64_t nq, int64_t ldq,
+                const float* ref, int64_t m, int64_t ldr,
+                int k, int sqrt_dist,
+                int64_t* idx_out, float* dist_out, void* stream);
+
+/* ------------------------------------------------------------------ FPS
+ * Farthest point sampling of one cloud, replaces torch_cluster.fps + torch.sort at
+ * model/modules.py:133-135.  Start point = start_idx (0 = deterministic, the
+ * reference's random_start=False); next = argmax of the running min squared distance
+ * (first maximum on ties).  Output is SORTED ascending (what the caller consumes).
+ *   xyz (n, ld>=3);  idx_sorted_out (n_out) int64;  order_out (n_out) int64 or NULL
+ *   (selection order, for tests).  workspace: o4d_fps_workspace_bytes(n, n_out). */
+size_t o4d_fps_workspace_bytes(int64_t n, int64_t n_out);
+int o4d_fps_f32(const float* xyz, int64_t n, int64_t ld, int64_t n_out, int64_t start_idx,
+                int64_t* idx_sorted_out, int64_t* order_out,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ dense layer
+ * C = post( pre(A) @ W^T + bias ) [+ R],  replaces every torch.nn.Linear on the path
+ * (cuBLAS SGEMM in the reference).  A (rows, k) lda; W (n, k) row-major exactly as
+ * nn.Linear stores it; bias (n) or NULL; R (rows, n) ldr or NULL (may alias C);
+ * flags: O4D_RELU_IN applies ReLU to A on load, O4D_RELU_OUT to the result before R.
+ * precision: 0 = fp32 CUDA-core FMA, 1 = tcgen05 bf16x3 split (fp32-grade), 2 = tcgen05
+ * single bf16 (fast, ~3e-3).  */
+#define O4D_RELU_IN 1
+#define O4D_RELU_OUT 2
+int o4d_linear_f32(const float* A, int64_t rows, int64_t k, int64_t lda,
+                   const float* W, const float* bias, int64_t n,
+                   const float* R, int64_t ldr,
+                   float* C, int64_t ldc, int flags, int precision, void* stream);
+
+/* ------------------------------------------------------------------ vector attention
+ * One PointTransformerBlock, model/modules.py:18-67 wrapping PointTransformerLayer,
+ * model/point_transformer_layer.py:116-183:
+ *   z = x + W3 . attn( W1 x + b1 ; pos ; x2 ; pos2 ) + b3
+ * self mode: x2 = NULL (keys/values are layer1(x) of the same cloud); cross mode: x2
+ * (m, d2) raw abstract features, pos2 (m, 3).
+ * Parameter table `p` (device pointers), in state_dict order:
+ *   0 layer1.weight (d,d_in) 1 layer1.bias  2 to_q.weight (d,d)  3 to_k.weight (d,d2)
+ *   4 to_v.weight (d,d2)  5 pos_mlp.0.weight (32,3)  6 pos_mlp.0.bias  7 pos_mlp.2.weight (d,32)
+ *   8 pos_mlp.2.bias  9 attn_mlp.0.weight (2d,d)  10 attn_mlp.0.bias  11 attn_mlp.2.weight (d,2d)
+ *   12 attn_mlp.2.bias  13 layer3.weight (d_out,d)  14 layer3.bias
+ * d_in == d == d_out in every configuration the reference builds (model.py:89-105,
+ * implicit.py:245-248); other shapes return O4D_E_UNSUPPORTED.
+ * knn_idx_out: optional (n, k) int64 copy of the neighbour indices. */
+#define O4D_PTBLOCK_NPARAMS 15
+size_t o4d_pt_block_workspace_bytes(int64_t n, int64_t m, int d, int d2, int k);
+int o4d_pt_block_forward(const float* const* p,
+                         const float* x, int64_t n, int d, const float* pos, int64_t ldpos,
+                         const float* x2, int64_t m, int d2, int64_t ldx2,
+                         const float* pos2, int64_t ldpos2,
+                         int k, int precision,
+                         float* z, int64_t* knn_idx_out,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ down transition
+ * DownTransition.forward, model/modules.py:113-163, one cloud:
+ *   idx = sort(fps(pos, ceil(n/factor)));  nbr = knn(pos[idx] -> pos, k)
+ *   y = relu( [LayerNorm]( W x + b ) ) on all n rows;  z = max over the k neighbour rows.
+ * params: 0 mlp.0.weight (d_out,d_in) 1 mlp.0.bias 2 mlp.1.weight|NULL 3 mlp.1.bias|NULL
+ * norm: 0 none, 1 LayerNorm(eps 1e-5).  ('batch' is unused by the released configs:
+ * O4D_E_UNSUPPORTED.)   Outputs z (n_out, d_out), pos_out (n_out, 3),
+ * fps_idx_out (n_out) int64 or NULL. */
+#define O4D_DOWN_NPARAMS 4
+size_t o4d_down_workspace_bytes(int64_t n, int d_in, int d_out, int factor, int k);
+int o4d_down_forward(const float* const* p, const float* x, int64_t n, int d_in,
+                     const float* pos, int64_t ldpos, int d_out, int factor, int k, int norm,
+                     int64_t start_idx, int precision,
+                     float* z, float* pos_out, int64_t* fps_idx_out,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ encoder
+ * PointCompletionNetV3.forward, model/model.py:148-233, one cloud (B = 1 per call;
+ * the host loops over the batch).  Supported = the released configuration:
+ * enable_decoder=0, skip_connections=0, output_featurized=1, output_global_emb=1. */
+typedef struct o4d_encoder_config {
+    int32_t d_in;             /* 8 */
+    int32_t d_feat;           /* 36 */
+    int32_t down_blocks;      /* 3 */
+    int32_t transition_factor;/* 3 */
+    int32_t pt_num_neighbors; /* 14 / 16 */
+    int32_t down_neighbors;   /* 12 */
+    int32_t norm;             /* 0 none, 1 layer */
+    int32_t abstract_levels;  /* 1 / 2 */
+    int32_t global_dim;       /* 128 */
+    int32_t precision;        /* see o4d_linear_f32 */
+} o4d_encoder_config;
+/* Parameter table order = state_dict order of the reference module (model.py:75-146):
+ *   pre_mlp.0.{w,b}, pre_mlp.2.{w,b}, global_mlp.0.{w,b}, global_mlp.2.{w,b},
+ *   abstract_skip_mlps.{j}.{w,b} (levels-1 of them),
+ *   then per block i: PT block -> its 15 tensors; Down -> mlp.0.{w,b}[, mlp.1.{w,b}].
+ * o4d_encoder_num_params() returns the expected count. */
+int o4d_encoder_num_params(const o4d_encoder_config* cfg);
+int64_t o4d_encoder_num_abstract(const o4d_encoder_config* cfg, int64_t n);
+size_t o4d_encoder_workspace_bytes(const o4d_encoder_config* cfg, int64_t n);
+/* pcl (n, d_in) -> abstract (M, 3 + d_feat*2^down_blocks), global (global_dim).
+ * start_idx_host: HOST array of down_blocks FPS start indices (one per down transition,
+ * each < the point count of its level) or NULL for all-zero = the reference's
+ * deterministic test-time setting fps_random_start=False (eval/inference.py:59).
+ * level_pos_out: optional array of down_blocks+1 device pointers receiving the
+ * coordinates at every level ((n_l,3) each; "layer_coords", model.py:161-199). */
+int o4d_encoder_forward(const o4d_encoder_config* cfg, const float* const* params,
+                        const float* pcl, int64_t n, const int64_t* start_idx_host,
+                        float* abstract_out, float* global_out, float* const* level_pos_out,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ decoder
+ * LocalPclResnetFC.forward / do_forward_attention, model/implicit.py:271-445
+ * (local_mode='attention', activation='relu', all cross layers type 'c', B = 1). */
+typedef struct o4d_decoder_config {
+    int32_t d_in;               /* 4 (x,y,z,t) */
+    int32_t d_hidden;           /* 416 */
+    int32_t d_out;              /* G */
+    int32_t d_latent;           /* 416 = global + local */
+    int32_t d_latent_local;     /* 288 */
+    int32_t n_blocks;           /* 6 */
+    int32_t pos_encoding_freqs; /* 8 */
+    int32_t num_local_features; /* 8 */
+    int32_t cross_attn_neighbors; /* 14 */
+    int32_t cross_attn_layers;  /* 2 */
+    int32_t precision;          /* see o4d_linear_f32 */
+} o4d_decoder_config;
+/* Parameter table order = state_dict order (implicit.py:142-150, 236-269):
+ *   lin_in.{w,b}, lin_out.{w,b}, blocks.{i}.fc_0.{w,b}, blocks.{i}.fc_1.{w,b} (i<n_blocks),
+ *   lin_z.{i}.{w,b} (i<n_blocks), pt_blocks.{j} -> 15 tensors each (j<cross_attn_layers). */
+int o4d_decoder_num_params(const o4d_decoder_config* cfg);
+
+/* Scene-constant state (K/V tables of every cross layer, global halves of lin_z, packed
+ * abstract coordinates); recomputed once per (weights, scene), reused by every query
+ * mini-batch of that scene (the reference recomputes all of it per mini-batch,
+ * point_transformer_layer.py:171-172, implicit.py:417).
+ *   scene buffer: caller-owned, o4d_decoder_scene_bytes(cfg, m) bytes. */
+size_t o4d_decoder_scene_bytes(const o4d_decoder_config* cfg, int64_t m);
+int o4d_decoder_prepare_scene(const o4d_decoder_config* cfg, const float* const* params,
+                              const float* pcl_abstract, int64_t m, int64_t ld_abstract,
+                              const float* feat_global,
+                              void* scene, size_t scene_bytes, void* stream);
+size_t o4d_decoder_workspace_bytes(const o4d_decoder_config* cfg, int64_t nq, int64_t m);
+/* query (nq, 4) -> out (nq, d_out), penult (nq, d_hidden) or NULL. */
+int o4d_decoder_forward(const o4d_decoder_config* cfg, const float* const* params,
+                        const void* scene, int64_t m,
+                        const float* query, int64_t nq,
+                        float* out, float* penult,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* Host-buffer convenience used for end-to-end timing and by non-torch callers:
+ * the eval/inference.py:204-246 mini-batch loop in one call.  query_host / out_host are
+ * (pinned or pageable) HOST buffers; device scratch is caller-owned
+ * (o4d_decoder_run_host_device_bytes).  Copies in, runs every mini-batch of
+ * `batch` queries, copies out, synchronises the stream before returning. */
+size_t o4d_decoder_run_host_device_bytes(const o4d_decoder_config* cfg, int64_t batch, int64_t m);
+int o4d_decoder_run_host(const o4d_decoder_config* cfg, const float* const* params,
+                         const void* scene, int64_t m,
+                         const float* query_host, int64_t nq, int64_t batch,
+                         float* out_host,
+                         void* device_scratch, size_t device_scratch_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* O4D_H_ */

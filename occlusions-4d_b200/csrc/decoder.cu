@@ -1,0 +1,259 @@
+// Implicit decoder orchestration: LocalPclResnetFC.forward + do_forward_attention,
+// model/implicit.py:271-445 (local_mode 'attention', ReLU, cross layers of type 'c', B = 1).
+//
+// Scene-constant work is hoisted into o4d_decoder_prepare_scene (the reference redoes it
+// for every query mini-batch): packed abstract coordinates/features, the K/V tables
+// to_k(x2), to_v(x2) of every cross layer (point_transformer_layer.py:171-172) and the
+// global half of every lin_z (implicit.py:417: lin_z(cat[global, local]) =
+// W[:, :Dg] g + b  +  W[:, Dg:] f_local; the first term is a per-scene vector).
+#include "o4d_common.cuh"
+
+namespace o4d {
+
+static bool dec_cfg_ok(const o4d_decoder_config* c) {
+    return c && c->d_in == 4 && c->d_hidden >= 1 && c->d_out >= 1 && c->d_latent == c->d_hidden &&
+           c->d_latent_local >= 1 && c->d_latent_local < c->d_latent && c->n_blocks >= 1 &&
+           c->n_blocks <= O4D_MAX_BLOCKS && c->pos_encoding_freqs >= 0 && c->pos_encoding_freqs <= 24 &&
+           c->num_local_features >= 1 && c->num_local_features <= O4D_MAX_K && c->cross_attn_neighbors >= 1 &&
+           c->cross_attn_neighbors <= O4D_MAX_K && c->cross_attn_layers >= 0 &&
+           c->cross_attn_layers <= O4D_MAX_BLOCKS && c->precision >= 0 && c->precision <= 2;
+}
+
+struct DecParams {
+    const float *lin_in_w, *lin_in_b, *lin_out_w, *lin_out_b;
+    const float *fc0_w[O4D_MAX_BLOCKS], *fc0_b[O4D_MAX_BLOCKS], *fc1_w[O4D_MAX_BLOCKS], *fc1_b[O4D_MAX_BLOCKS];
+    const float *z_w[O4D_MAX_BLOCKS], *z_b[O4D_MAX_BLOCKS];
+    const float* const* pt[O4D_MAX_BLOCKS];
+    int use_pt[O4D_MAX_BLOCKS];  // block -> cross layer index or -1 (implicit.py:265-269)
+};
+
+static void dec_unpack(const o4d_decoder_config* c, const float* const* P, DecParams* d) {
+    int i = 0;
+    d->lin_in_w = P[i++]; d->lin_in_b = P[i++];
+    d->lin_out_w = P[i++]; d->lin_out_b = P[i++];
+    for (int b = 0; b < c->n_blocks; ++b) {
+        d->fc0_w[b] = P[i++]; d->fc0_b[b] = P[i++];
+        d->fc1_w[b] = P[i++]; d->fc1_b[b] = P[i++];
+    }
+    for (int b = 0; b < c->n_blocks; ++b) {
+        d->z_w[b] = P[i++]; d->z_b[b] = P[i++];
+    }
+    for (int b = 0; b < c->n_blocks; ++b) d->use_pt[b] = -1;
+    for (int j = 0; j < c->cross_attn_layers; ++j) {
+        d->pt[j] = P + i;
+        i += O4D_PTBLOCK_NPARAMS;
+        int at = ((j + 1) * c->n_blocks) / (c->cross_attn_layers + 1);
+        if (at < c->n_blocks) d->use_pt[at] = j;  // later layers win a collision, like the dict at :269
+    }
+}
+
+struct SceneView {
+    float* abs_xyz;   // (m, 3)
+    float* abs_feat;  // (m, E)
+    float* zg;        // (n_blocks, H)   W_z[:, :Dg] g + b_z
+    float* ktab[O4D_MAX_BLOCKS];  // (m, H) per cross layer
+    float* vtab[O4D_MAX_BLOCKS];
+    size_t bytes;
+};
+
+static SceneView scene_view(const o4d_decoder_config* c, int64_t m, void* base) {
+    Arena a(base ? base : nullptr, base ? (size_t)-1 : 0);
+    SceneView s;
+    s.abs_xyz = a.get<float>((size_t)m * 3);
+    s.abs_feat = a.get<float>((size_t)m * c->d_latent_local);
+    s.zg = a.get<float>((size_t)c->n_blocks * c->d_hidden);
+    for (int j = 0; j < c->cross_attn_layers; ++j) {
+        s.ktab[j] = a.get<float>((size_t)m * c->d_hidden);
+        s.vtab[j] = a.get<float>((size_t)m * c->d_hidden);
+    }
+    s.bytes = a.off;
+    return s;
+}
+
+int decoder_prepare(const o4d_decoder_config* c, const float* const* P, const float* pcl_abstract, int64_t m,
+                    int64_t ld, const float* feat_global, void* scene, size_t scene_bytes, cudaStream_t st) {
+    O4D_REQUIRE(dec_cfg_ok(c), "decoder: invalid configuration");
+    O4D_REQUIRE(P && pcl_abstract && feat_global && scene, "decoder prepare: null pointer");
+    const int E = c->d_latent_local, H = c->d_hidden, Dg = c->d_latent - c->d_latent_local;
+    O4D_REQUIRE(m >= 1 && ld >= 3 + E, "decoder prepare: abstract cloud must be (m, >= 3 + %d)", E);
+    O4D_REQUIRE(m >= c->num_local_features && (c->cross_attn_layers == 0 || m >= c->cross_attn_neighbors),
+                "decoder prepare: abstract cloud of %lld points is smaller than the neighbour count", (long long)m);
+    SceneView s = scene_view(c, m, scene);
+    if (scene_bytes < s.bytes) {
+        set_error("decoder prepare: scene buffer too small (%zu < %zu)", scene_bytes, s.bytes);
+        return O4D_E_WORKSPACE;
+    }
+    DecParams d;
+    dec_unpack(c, P, &d);
+    O4D_TRY(copy2d_launch(pcl_abstract, ld, m, 3, s.abs_xyz, 3, st));          // implicit.py:288
+    O4D_TRY(copy2d_launch(pcl_abstract + 3, ld, m, E, s.abs_feat, E, st));     // implicit.py:289
+    for (int b = 0; b < c->n_blocks; ++b) {
+        O4D_TRY(linear_ldw_launch(feat_global, 1, Dg, Dg, d.z_w[b], c->d_latent, d.z_b[b], H, nullptr, 0,
+                                  s.zg + (size_t)b * H, H, 0, 0, st));
+    }
+    for (int j = 0; j < c->cross_attn_layers; ++j) {
+        PtBlockParams pp = PtBlockParams::from(d.pt[j]);
+        O4D_TRY(linear_launch(s.abs_feat, m, E, E, pp.wk, nullptr, H, nullptr, 0, s.ktab[j], H, 0, 0, st));
+        O4D_TRY(linear_launch(s.abs_feat, m, E, E, pp.wv, nullptr, H, nullptr, 0, s.vtab[j], H, 0, 0, st));
+    }
+    return 0;
+}
+
+struct DecWs {
+    int32_t *idx_l, *idx_c;
+    float *dist_l, *f_loc, *pe, *x, *h, *y;
+    char* sub;
+    size_t sub_bytes, bytes;
+};
+
+static DecWs dec_ws(const o4d_decoder_config* c, int64_t nq, void* base, size_t cap) {
+    Arena a(base, cap);
+    DecWs w;
+    const int H = c->d_hidden;
+    const int pe_w = c->d_in * (2 * c->pos_encoding_freqs + 1);
+    w.idx_l = a.get<int32_t>((size_t)nq * c->num_local_features);
+    w.dist_l = a.get<float>((size_t)nq * c->num_local_features);
+    w.idx_c = a.get<int32_t>((size_t)nq * c->cross_attn_neighbors);
+    w.f_loc = a.get<float>((size_t)nq * c->d_latent_local);
+    w.pe = a.get<float>((size_t)nq * pe_w);
+    w.x = a.get<float>((size_t)nq * H);
+    w.h = a.get<float>((size_t)nq * H);
+    w.y = a.get<float>((size_t)nq * H);
+    w.sub_bytes = c->cross_attn_layers > 0 ? attn_core_workspace_bytes(nq, H, c->cross_attn_neighbors) : 0;
+    w.sub = a.get<char>(w.sub_bytes);
+    w.bytes = a.off;
+    if (!a.ok) w.x = nullptr;
+    return w;
+}
+
+int decoder_forward(const o4d_decoder_config* c, const float* const* P, const void* scene, int64_t m,
+                    const float* query, int64_t nq, float* out, float* penult, void* ws, size_t ws_bytes,
+                    cudaStream_t st) {
+    O4D_REQUIRE(dec_cfg_ok(c), "decoder: invalid configuration");
+    O4D_REQUIRE(P && scene && out, "decoder forward: null pointer");
+    O4D_REQUIRE(nq >= 0 && m >= 1, "decoder forward: bad sizes");
+    if (nq == 0) return 0;
+    O4D_REQUIRE(query != nullptr, "decoder forward: null query");
+    const int H = c->d_hidden, E = c->d_latent_local, Dg = c->d_latent - E;
+    const int prec = c->precision;
+    const int pe_w = c->d_in * (2 * c->pos_encoding_freqs + 1);
+    SceneView s = scene_view(c, m, const_cast<void*>(scene));
+    DecWs w = dec_ws(c, nq, ws, ws_bytes);
+    if (!ws || !w.x) {
+        set_error("decoder forward: workspace too small (%zu < %zu)", ws_bytes, w.bytes);
+        return O4D_E_WORKSPACE;
+    }
+    DecParams d;
+    dec_unpack(c, P, &d);
+
+    // implicit.py:328-339  K_l nearest abstract points, inverse-distance blend of their features
+    O4D_TRY(knn_launch(query, nq, c->d_in, s.abs_xyz, m, 3, c->num_local_features, 1, w.idx_l, nullptr, w.dist_l, st));
+    O4D_TRY(local_blend_launch(w.idx_l, w.dist_l, s.abs_feat, E, nq, c->num_local_features, E, w.f_loc, E, st));
+    // point_transformer_layer.py:167 -- identical for every cross layer (same query / abstract cloud)
+    if (c->cross_attn_layers > 0)
+        O4D_TRY(knn_launch(query, nq, c->d_in, s.abs_xyz, m, 3, c->cross_attn_neighbors, 0, w.idx_c, nullptr, nullptr, st));
+    // implicit.py:403-408
+    if (c->pos_encoding_freqs > 0) {
+        O4D_TRY(posenc_launch(query, nq, c->d_in, c->pos_encoding_freqs, w.pe, st));
+        O4D_TRY(linear_launch(w.pe, nq, pe_w, pe_w, d.lin_in_w, d.lin_in_b, H, nullptr, 0, w.x, H, 0, prec, st));
+    } else {
+        O4D_TRY(linear_launch(query, nq, c->d_in, c->d_in, d.lin_in_w, d.lin_in_b, H, nullptr, 0, w.x, H, 0, prec, st));
+    }
+    for (int b = 0; b < c->n_blocks; ++b) {
+        // implicit.py:416-418  x += lin_z(features_query)   (global half pre-reduced into zg)
+        O4D_TRY(linear_ldw_launch(w.f_loc, nq, E, E, d.z_w[b] + Dg, c->d_latent, s.zg + (size_t)b * H, H, w.x, H,
+                                  w.x, H, 0, prec, st));
+        // implicit.py:93-101  x += fc_1(relu(fc_0(relu(x))))
+        O4D_TRY(linear_launch(w.x, nq, H, H, d.fc0_w[b], d.fc0_b[b], H, nullptr, 0, w.h, H, O4D_RELU_IN, prec, st));
+        O4D_TRY(linear_launch(w.h, nq, H, H, d.fc1_w[b], d.fc1_b[b], H, w.x, H, w.x, H, O4D_RELU_IN, prec, st));
+        if (d.use_pt[b] >= 0) {
+            // implicit.py:421-439 -> modules.py:61-65 cross attention onto the abstract cloud
+            const int j = d.use_pt[b];
+            PtBlockParams pp = PtBlockParams::from(d.pt[j]);
+            O4D_TRY(linear_launch(w.x, nq, H, H, pp.w1, pp.b1, H, nullptr, 0, w.y, H, 0, prec, st));
+            O4D_TRY(linear_launch(w.y, nq, H, H, pp.wq, nullptr, H, nullptr, 0, w.h, H, 0, prec, st));
+            O4D_TRY(attn_core_launch(pp, w.h, s.ktab[j], s.vtab[j], query, c->d_in, s.abs_xyz, 3, w.idx_c, nq, H,
+                                     c->cross_attn_neighbors, w.x, w.x, prec, w.sub, w.sub_bytes, st));
+        }
+    }
+    if (penult) O4D_TRY(copy2d_launch(w.x, H, nq, H, penult, H, st));           // implicit.py:441
+    // implicit.py:442-443
+    return linear_launch(w.x, nq, H, H, d.lin_out_w, d.lin_out_b, c->d_out, nullptr, 0, out, c->d_out, O4D_RELU_IN,
+                         prec, st);
+}
+
+}  // namespace o4d
+
+extern "C" int o4d_decoder_num_params(const o4d_decoder_config* c) {
+    if (!o4d::dec_cfg_ok(c)) return O4D_E_ARG;
+    return 4 + 6 * c->n_blocks + O4D_PTBLOCK_NPARAMS * c->cross_attn_layers;
+}
+
+extern "C" size_t o4d_decoder_scene_bytes(const o4d_decoder_config* c, int64_t m) {
+    if (!o4d::dec_cfg_ok(c) || m < 1) return 0;
+    return o4d::scene_view(c, m, nullptr).bytes;
+}
+
+extern "C" int o4d_decoder_prepare_scene(const o4d_decoder_config* cfg, const float* const* params,
+                                         const float* pcl_abstract, int64_t m, int64_t ld_abstract,
+                                         const float* feat_global, void* scene, size_t scene_bytes, void* stream) {
+    return o4d::decoder_prepare(cfg, params, pcl_abstract, m, ld_abstract, feat_global, scene, scene_bytes,
+                                (cudaStream_t)stream);
+}
+
+extern "C" size_t o4d_decoder_workspace_bytes(const o4d_decoder_config* c, int64_t nq, int64_t m) {
+    (void)m;
+    if (!o4d::dec_cfg_ok(c) || nq < 1) return 0;
+    return o4d::dec_ws(c, nq, nullptr, 0).bytes;
+}
+
+extern "C" int o4d_decoder_forward(const o4d_decoder_config* cfg, const float* const* params, const void* scene,
+                                   int64_t m, const float* query, int64_t nq, float* out, float* penult,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
+    return o4d::decoder_forward(cfg, params, scene, m, query, nq, out, penult, workspace, workspace_bytes,
+                                (cudaStream_t)stream);
+}
+
+extern "C" size_t o4d_decoder_run_host_device_bytes(const o4d_decoder_config* c, int64_t batch, int64_t m) {
+    if (!o4d::dec_cfg_ok(c) || batch < 1) return 0;
+    // double-buffered query / output staging + one forward workspace
+    size_t stage = 2 * (o4d::align_up((size_t)batch * 4 * sizeof(float), 256) +
+                        o4d::align_up((size_t)batch * c->d_out * sizeof(float), 256));
+    return stage + o4d_decoder_workspace_bytes(c, batch, m);
+}
+
+extern "C" int o4d_decoder_run_host(const o4d_decoder_config* c, const float* const* params, const void* scene,
+                                    int64_t m, const float* query_host, int64_t nq, int64_t batch, float* out_host,
+                                    void* device_scratch, size_t device_scratch_bytes, void* stream) {
+    using namespace o4d;
+    O4D_REQUIRE(dec_cfg_ok(c), "decoder: invalid configuration");
+    O4D_REQUIRE(query_host && out_host && device_scratch && batch >= 1 && nq >= 0, "decoder run_host: bad argument");
+    if (device_scratch_bytes < o4d_decoder_run_host_device_bytes(c, batch, m)) {
+        set_error("decoder run_host: device scratch too small");
+        return O4D_E_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    Arena a(device_scratch, device_scratch_bytes);
+    float* qd[2];
+    float* od[2];
+    for (int i = 0; i < 2; ++i) {
+        qd[i] = a.get<float>((size_t)batch * 4);
+        od[i] = a.get<float>((size_t)batch * c->d_out);
+    }
+    void* ws = (char*)device_scratch + a.off;
+    const size_t ws_bytes = device_scratch_bytes - a.off;
+    // eval/inference.py:204-246: H2D of the mini-batch, forward, D2H of the result.  All on one
+    // stream (the copies are tiny next to the forward); buffers alternate so a pinned-host
+    // caller gets copy/compute overlap from the copy engines without extra streams here.
+    int slot = 0;
+    for (int64_t s0 = 0; s0 < nq; s0 += batch, slot ^= 1) {
+        const int64_t nb = (nq - s0 < batch) ? (nq - s0) : batch;
+        O4D_CUDA(cudaMemcpyAsync(qd[slot], query_host + s0 * 4, (size_t)nb * 4 * sizeof(float),
+                                 cudaMemcpyHostToDevice, st));
+        O4D_TRY(decoder_forward(c, params, scene, m, qd[slot], nb, od[slot], nullptr, ws, ws_bytes, st));
+        O4D_CUDA(cudaMemcpyAsync(out_host + s0 * c->d_out, od[slot], (size_t)nb * c->d_out * sizeof(float),
+                                 cudaMemcpyDeviceToHost, st));
+    }
+    O4D_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}

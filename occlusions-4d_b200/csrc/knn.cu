@@ -1,0 +1,182 @@
+// Brute-force 3-D kNN without materialising the (nq, m) distance matrix.
+//
+// Replaces  kNN_torch        model/point_transformer_layer.py:76-99  (square_distance + argsort)
+//           my_knn_torch     utils/geometry.py:458-503               (norm + topk)
+//           torch_cluster.knn at model/modules.py:142-146
+//
+// Layout: reference points are staged through shared memory as SoA tiles (x[], y[], z[]);
+// every query is served by S adjacent lanes of a warp ("sub-lanes"), each scanning the
+// tile with stride S and keeping its own ascending top-KMAX list in registers; the S lists
+// are merged with warp shuffles.  Ordering is ascending (distance, index), distance =
+// fp32 ((dx*dx + dy*dy) + dz*dz) with every operation rounded (no FMA contraction),
+// optionally square-rooted (sqrt is monotone but merges neighbouring values, so the
+// Euclidean ordering is evaluated on the rooted value to honour the index tie-break).
+#include "o4d_common.cuh"
+#include <math_constants.h>
+
+namespace o4d {
+
+constexpr int KNN_THREADS = 256;
+constexpr int KNN_TILE = 2048;  // reference points per shared-memory tile (24 KB)
+
+template <int KMAX>
+struct TopK {
+    float d[KMAX];
+    int i[KMAX];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int t = 0; t < KMAX; ++t) {
+            d[t] = CUDART_INF_F;
+            i[t] = 0x7fffffff;
+        }
+    }
+    // candidates arrive in ascending index order within one thread, so a strict
+    // comparison keeps the lower index ahead of an equal distance.
+    __device__ __forceinline__ void push(float dist, int idx) {
+        if (dist < d[KMAX - 1]) {
+            d[KMAX - 1] = dist;
+            i[KMAX - 1] = idx;
+#pragma unroll
+            for (int t = KMAX - 1; t > 0; --t) {
+                if (d[t] < d[t - 1]) {
+                    float td = d[t]; d[t] = d[t - 1]; d[t - 1] = td;
+                    int ti = i[t]; i[t] = i[t - 1]; i[t - 1] = ti;
+                }
+            }
+        }
+    }
+    __device__ __forceinline__ void pop_front() {
+#pragma unroll
+        for (int t = 0; t < KMAX - 1; ++t) {
+            d[t] = d[t + 1];
+            i[t] = i[t + 1];
+        }
+        d[KMAX - 1] = CUDART_INF_F;
+        i[KMAX - 1] = 0x7fffffff;
+    }
+};
+
+template <int KMAX, int S, bool SQRT>
+__global__ void __launch_bounds__(KNN_THREADS)
+knn_kernel(const float* __restrict__ query, int64_t nq, int64_t ldq,
+           const float* __restrict__ ref, int m, int64_t ldr, int k,
+           int32_t* __restrict__ idx32, int64_t* __restrict__ idx64, float* __restrict__ dist_out) {
+    __shared__ float sx[KNN_TILE], sy[KNN_TILE], sz[KNN_TILE];
+    constexpr int QPB = KNN_THREADS / S;  // queries per block
+    const int sub = threadIdx.x % S;
+    const int64_t qi = (int64_t)blockIdx.x * QPB + threadIdx.x / S;
+    const bool live = qi < nq;
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    if (live) {
+        qx = query[qi * ldq + 0];
+        qy = query[qi * ldq + 1];
+        qz = query[qi * ldq + 2];
+    }
+    TopK<KMAX> top;
+    top.init();
+
+    for (int base = 0; base < m; base += KNN_TILE) {
+        const int cnt = min(KNN_TILE, m - base);
+        __syncthreads();
+        for (int t = threadIdx.x; t < cnt; t += KNN_THREADS) {
+            const float* r = ref + (int64_t)(base + t) * ldr;
+            sx[t] = r[0];
+            sy[t] = r[1];
+            sz[t] = r[2];
+        }
+        __syncthreads();
+        if (live) {
+            for (int t = sub; t < cnt; t += S) {
+                float dx = qx - sx[t], dy = qy - sy[t], dz = qz - sz[t];
+                float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                if (SQRT) d2 = __fsqrt_rn(d2);
+                top.push(d2, base + t);
+            }
+        }
+    }
+
+    // merge the S sub-lane lists: k rounds of "global minimum of the heads".
+    const unsigned full = 0xffffffffu;
+    for (int r = 0; r < k; ++r) {
+        float bd = top.d[0];
+        int bi = top.i[0];
+        if (S > 1) {
+#pragma unroll
+            for (int off = S / 2; off > 0; off >>= 1) {
+                float od = __shfl_xor_sync(full, bd, off);
+                int oi = __shfl_xor_sync(full, bi, off);
+                if (od < bd || (od == bd && oi < bi)) {
+                    bd = od;
+                    bi = oi;
+                }
+            }
+            if (top.i[0] == bi && top.d[0] == bd) top.pop_front();
+        } else {
+            top.pop_front();
+        }
+        if (live && sub == 0) {
+            if (idx32) idx32[qi * k + r] = bi;
+            if (idx64) idx64[qi * k + r] = (int64_t)bi;
+            if (dist_out) dist_out[qi * k + r] = bd;
+        }
+    }
+}
+
+template <int KMAX, bool SQRT>
+static int knn_dispatch_s(int S, dim3 grid_unused, const float* query, int64_t nq, int64_t ldq,
+                          const float* ref, int m, int64_t ldr, int k, int32_t* idx32,
+                          int64_t* idx64, float* dist, cudaStream_t st) {
+    (void)grid_unused;
+#define O4D_KNN_CASE(SV)                                                                         \
+    case SV: {                                                                                   \
+        int64_t blocks = cdiv(nq, KNN_THREADS / SV);                                             \
+        knn_kernel<KMAX, SV, SQRT><<<(unsigned)blocks, KNN_THREADS, 0, st>>>(                    \
+            query, nq, ldq, ref, m, ldr, k, idx32, idx64, dist);                                 \
+        break;                                                                                   \
+    }
+    switch (S) {
+        O4D_KNN_CASE(1)
+        O4D_KNN_CASE(4)
+        O4D_KNN_CASE(32)
+        default:
+            set_error("knn: bad sub-lane count %d", S);
+            return O4D_E_ARG;
+    }
+#undef O4D_KNN_CASE
+    O4D_LAUNCH_CHECK();
+    return 0;
+}
+
+int knn_launch(const float* query, int64_t nq, int64_t ldq, const float* ref, int64_t m,
+               int64_t ldr, int k, int sqrt_dist, int32_t* idx32, int64_t* idx64, float* dist,
+               cudaStream_t st) {
+    O4D_REQUIRE(query && ref, "knn: null input");
+    O4D_REQUIRE(idx32 || idx64 || dist, "knn: no output requested");
+    O4D_REQUIRE(ldq >= 3 && ldr >= 3, "knn: leading dimensions must be >= 3");
+    O4D_REQUIRE(k >= 1 && k <= O4D_MAX_K, "knn: k=%d outside [1,%d]", k, O4D_MAX_K);
+    O4D_REQUIRE(m >= k && m < (int64_t)0x7fffffff, "knn: need k <= m < 2^31 (m=%lld, k=%d)",
+                (long long)m, k);
+    O4D_REQUIRE(nq >= 0, "knn: negative query count");
+    if (nq == 0) return 0;
+    // enough threads to cover the machine (148 SMs x 2048 resident threads) a few times.
+    int S = 1;
+    if (nq * 1 < 600000 && m >= 128) S = 4;
+    if (nq * 4 < 600000 && m >= 1024) S = 32;
+    dim3 g;
+    if (k <= 8) {
+        return sqrt_dist ? knn_dispatch_s<8, true>(S, g, query, nq, ldq, ref, (int)m, ldr, k, idx32, idx64, dist, st)
+                         : knn_dispatch_s<8, false>(S, g, query, nq, ldq, ref, (int)m, ldr, k, idx32, idx64, dist, st);
+    }
+    return sqrt_dist ? knn_dispatch_s<16, true>(S, g, query, nq, ldq, ref, (int)m, ldr, k, idx32, idx64, dist, st)
+                     : knn_dispatch_s<16, false>(S, g, query, nq, ldq, ref, (int)m, ldr, k, idx32, idx64, dist, st);
+}
+
+}  // namespace o4d
+
+extern "C" int o4d_knn_f32(const float* query, int64_t nq, int64_t ldq, const float* ref, int64_t m,
+                           int64_t ldr, int k, int sqrt_dist, int64_t* idx_out, float* dist_out,
+                           void* stream) {
+    O4D_REQUIRE(idx_out || dist_out, "o4d_knn_f32: no output requested");
+    return o4d::knn_launch(query, nq, ldq, ref, m, ldr, k, sqrt_dist, nullptr, idx_out, dist_out,
+                           (cudaStream_t)stream);
+}

@@ -1,0 +1,224 @@
+// Small bandwidth-bound kernels of the path: Fourier encoding, inverse-distance feature
+// blend, neighbourhood max-pool, LayerNorm+ReLU, row gathers, column mean.
+#include "o4d_common.cuh"
+
+namespace o4d {
+
+// positional_encode, model/implicit.py:20-43 with base_frequency 0.1 (:184,:405).
+// out (n, d_in*(2F+1)): raw coords, then per power p: sin(w_p x) [d_in], cos(w_p x) [d_in].
+// omega is formed in double like the reference's Python scalar and rounded to fp32 when it
+// multiplies the fp32 tensor (torch scalar-multiply semantics); sinf/cosf are the
+// accurate versions (arguments reach ~4e3 rad) -- this file is built without fast-math.
+__global__ void posenc_kernel(const float* __restrict__ q, int64_t n, int d_in, int n_freq,
+                              float* __restrict__ out) {
+    const int width = d_in * (2 * n_freq + 1);
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n * width) return;
+    const int64_t i = e / width;
+    const int c = (int)(e % width);
+    float v;
+    if (c < d_in) {
+        v = q[i * d_in + c];
+    } else {
+        const int t = c - d_in;
+        const int p = t / (2 * d_in);
+        const int r = t % (2 * d_in);
+        const double omega_d = 0.1 * (double)(1 << p) * 3.141592653589793 * 2.0;
+        const float omega = (float)omega_d;
+        const float arg = q[i * d_in + (r % d_in)] * omega;
+        v = (r < d_in) ? sinf(arg) : cosf(arg);
+    }
+    out[e] = v;
+}
+
+int posenc_launch(const float* q, int64_t n, int d_in, int n_freq, float* out, cudaStream_t st) {
+    if (n == 0) return 0;
+    O4D_REQUIRE(n_freq >= 0 && n_freq <= 24, "posenc: bad frequency count %d", n_freq);
+    const int64_t total = n * d_in * (2 * n_freq + 1);
+    posenc_kernel<<<(unsigned)cdiv(total, 256), 256, 0, st>>>(q, n, d_in, n_freq, out);
+    O4D_LAUNCH_CHECK();
+    return 0;
+}
+
+// model/implicit.py:337-339: w = 1/(dist+1e-4); w /= sum|w| (F.normalize p=1, eps 1e-12);
+// out_i = sum_k w_k feat[idx_k].  One warp per query, lanes stride over channels.
+__global__ void __launch_bounds__(256)
+local_blend_kernel(const int32_t* __restrict__ idx, const float* __restrict__ dist,
+                   const float* __restrict__ feat, int64_t ldfeat, int64_t n, int k, int e,
+                   float* __restrict__ out, int64_t ldout) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n) return;
+    float w[O4D_MAX_K];
+    int id[O4D_MAX_K];
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < O4D_MAX_K; ++j) {
+        if (j < k) {
+            w[j] = 1.0f / (dist[i * k + j] + 1e-4f);
+            id[j] = idx[i * k + j];
+            sum += fabsf(w[j]);
+        }
+    }
+    const float denom = fmaxf(sum, 1e-12f);
+    for (int c = lane; c < e; c += 32) {
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < O4D_MAX_K; ++j) {
+            if (j < k) acc = fmaf(w[j] / denom, feat[(int64_t)id[j] * ldfeat + c], acc);
+        }
+        out[i * ldout + c] = acc;
+    }
+}
+
+int local_blend_launch(const int32_t* idx, const float* dist, const float* feat, int64_t ldfeat,
+                       int64_t n, int k, int e, float* out, int64_t ldout, cudaStream_t st) {
+    if (n == 0) return 0;
+    O4D_REQUIRE(k >= 1 && k <= O4D_MAX_K, "local blend: k=%d outside [1,%d]", k, O4D_MAX_K);
+    local_blend_kernel<<<(unsigned)cdiv(n, 8), 256, 0, st>>>(idx, dist, feat, ldfeat, n, k, e, out, ldout);
+    O4D_LAUNCH_CHECK();
+    return 0;
+}
+
+// model/modules.py:156-158: z_i = max_j y[nbr[i,j]].
+__global__ void gather_max_kernel(const float* __restrict__ y, int64_t ldy, const int32_t* __restrict__ nbr,
+                                  int64_t n_out, int k, int d, float* __restrict__ z) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_out * d) return;
+    const int64_t i = e / d;
+    const int c = (int)(e % d);
+    float m = y[(int64_t)nbr[i * k] * ldy + c];
+    for (int j = 1; j < k; ++j) m = fmaxf(m, y[(int64_t)nbr[i * k + j] * ldy + c]);
+    z[e] = m;
+}
+
+int gather_max_launch(const float* y, int64_t ldy, const int32_t* nbr, int64_t n_out, int k, int d,
+                      float* z, cudaStream_t st) {
+    if (n_out == 0) return 0;
+    gather_max_kernel<<<(unsigned)cdiv(n_out * d, 256), 256, 0, st>>>(y, ldy, nbr, n_out, k, d, z);
+    O4D_LAUNCH_CHECK();
+    return 0;
+}
+
+// torch.nn.LayerNorm(d) (biased variance, eps inside the sqrt) followed by ReLU, in place.
+// One warp per row (model/modules.py:107-110 via :152).
+__global__ void __launch_bounds__(256)
+layernorm_relu_kernel(float* __restrict__ y, int64_t rows, int d, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, float eps) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    float* row = y + r * d;
+    float s = 0.f;
+    for (int c = lane; c < d; c += 32) s += row[c];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    const float mean = s / (float)d;
+    float v = 0.f;
+    for (int c = lane; c < d; c += 32) {
+        float t = row[c] - mean;
+        v = fmaf(t, t, v);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    const float rstd = rsqrtf(v / (float)d + eps);
+    for (int c = lane; c < d; c += 32) {
+        float t = (row[c] - mean) * rstd * gamma[c] + beta[c];
+        row[c] = fmaxf(t, 0.f);
+    }
+}
+
+int layernorm_relu_launch(float* y, int64_t rows, int d, const float* gamma, const float* beta,
+                          float eps, cudaStream_t st) {
+    if (rows == 0) return 0;
+    layernorm_relu_kernel<<<(unsigned)cdiv(rows, 8), 256, 0, st>>>(y, rows, d, gamma, beta, eps);
+    O4D_LAUNCH_CHECK();
+    return 0;
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ src, int64_t ldsrc, const int32_t* __restrict__ idx,
+                                   int64_t n, int d, float* __restrict__ dst, int64_t lddst) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n * d) return;
+    const int64_t i = e / d;
+    const int c = (int)(e % d);
+    dst[i * lddst + c] = src[(int64_t)idx[i] * ldsrc + c];
+}
+
+int gather_rows_launch(const float* src, int64_t ldsrc, const int32_t* idx, int64_t n, int d, float* dst,
+                       int64_t lddst, cudaStream_t st) {
+    if (n == 0) return 0;
+    gather_rows_kernel<<<(unsigned)cdiv(n * d, 256), 256, 0, st>>>(src, ldsrc, idx, n, d, dst, lddst);
+    O4D_LAUNCH_CHECK();
+    return 0;
+}
+
+// torch.mean(x, dim=points), model/model.py:189.  One block per 32 channels; rows are
+// split over the 8 warps and combined through shared memory (fixed order: deterministic).
+__global__ void __launch_bounds__(256)
+col_mean_kernel(const float* __restrict__ x, int64_t rows, int d, float* __restrict__ out) {
+    __shared__ float part[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + lane;
+    float s = 0.f;
+    if (c < d)
+        for (int64_t r = warp; r < rows; r += 8) s += x[r * d + c];
+    part[warp][lane] = s;
+    __syncthreads();
+    if (warp == 0 && c < d) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += part[w][lane];
+        out[c] = t / (float)rows;
+    }
+}
+
+int col_mean_launch(const float* x, int64_t rows, int d, float* out, cudaStream_t st) {
+    O4D_REQUIRE(rows >= 1, "mean over an empty cloud");
+    col_mean_kernel<<<(unsigned)cdiv(d, 32), 256, 0, st>>>(x, rows, d, out);
+    O4D_LAUNCH_CHECK();
+    return 0;
+}
+
+__global__ void copy2d_kernel(const float* __restrict__ src, int64_t ldsrc, int64_t rows, int cols,
+                              float* __restrict__ dst, int64_t lddst) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= rows * cols) return;
+    const int64_t r = e / cols;
+    const int c = (int)(e % cols);
+    dst[r * lddst + c] = src[r * ldsrc + c];
+}
+
+int copy2d_launch(const float* src, int64_t ldsrc, int64_t rows, int cols, float* dst, int64_t lddst,
+                  cudaStream_t st) {
+    if (rows == 0 || cols == 0) return 0;
+    copy2d_kernel<<<(unsigned)cdiv(rows * cols, 256), 256, 0, st>>>(src, ldsrc, rows, cols, dst, lddst);
+    O4D_LAUNCH_CHECK();
+    return 0;
+}
+
+__global__ void fill_col_kernel(float* __restrict__ dst, int64_t ld, int64_t rows, int col, float value) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < rows) dst[r * ld + col] = value;
+}
+
+int fill_col_launch(float* dst, int64_t ld, int64_t rows, int col, float value, cudaStream_t st) {
+    if (rows == 0) return 0;
+    fill_col_kernel<<<(unsigned)cdiv(rows, 256), 256, 0, st>>>(dst, ld, rows, col, value);
+    O4D_LAUNCH_CHECK();
+    return 0;
+}
+
+__global__ void widen_idx_kernel(const int32_t* __restrict__ in, int64_t count, int64_t* __restrict__ out) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < count) out[e] = in[e];
+}
+
+int widen_idx_launch(const int32_t* in, int64_t count, int64_t* out, cudaStream_t st) {
+    if (count == 0) return 0;
+    widen_idx_kernel<<<(unsigned)cdiv(count, 256), 256, 0, st>>>(in, count, out);
+    O4D_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace o4d

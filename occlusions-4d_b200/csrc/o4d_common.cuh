@@ -1,0 +1,136 @@
+// Shared helpers for libo4d.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/o4d.h"
+
+namespace o4d {
+
+void set_error(const char* fmt, ...);
+
+#define O4D_REQUIRE(cond, ...)                         \
+    do {                                               \
+        if (!(cond)) {                                 \
+            ::o4d::set_error(__VA_ARGS__);             \
+            return O4D_E_ARG;                          \
+        }                                              \
+    } while (0)
+
+#define O4D_CUDA(expr)                                                              \
+    do {                                                                            \
+        cudaError_t e__ = (expr);                                                   \
+        if (e__ != cudaSuccess) {                                                   \
+            ::o4d::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                             __FILE__, __LINE__);                                   \
+            return (int)e__;                                                        \
+        }                                                                           \
+    } while (0)
+
+#define O4D_LAUNCH_CHECK()                                                          \
+    do {                                                                            \
+        cudaError_t e__ = cudaGetLastError();                                       \
+        if (e__ != cudaSuccess) {                                                   \
+            ::o4d::set_error("kernel launch failed: %s (%s:%d)",                    \
+                             cudaGetErrorString(e__), __FILE__, __LINE__);          \
+            return (int)e__;                                                        \
+        }                                                                           \
+    } while (0)
+
+#define O4D_TRY(expr)                  \
+    do {                               \
+        int rc__ = (expr);             \
+        if (rc__ != 0) return rc__;    \
+    } while (0)
+
+static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Bump allocator over a caller-owned workspace.  With base == nullptr it only measures.
+struct Arena {
+    char* base;
+    size_t cap;
+    size_t off;
+    bool ok;
+    Arena(void* b, size_t c) : base((char*)b), cap(c), off(0), ok(true) {}
+    template <typename T>
+    T* get(size_t count) {
+        size_t bytes = align_up(count * sizeof(T), 256);
+        size_t start = off;
+        off += bytes;
+        if (base == nullptr) return nullptr;
+        if (off > cap) {
+            ok = false;
+            return nullptr;
+        }
+        return (T*)(base + start);
+    }
+};
+
+// ---- internal launchers shared between translation units (all async on `st`) ----
+int knn_launch(const float* query, int64_t nq, int64_t ldq, const float* ref, int64_t m,
+               int64_t ldr, int k, int sqrt_dist, int32_t* idx32, int64_t* idx64, float* dist,
+               cudaStream_t st);
+int fps_launch(const float* xyz, int64_t n, int64_t ld, int64_t n_out, int64_t start,
+               int32_t* idx_sorted32, int64_t* idx_sorted64, int64_t* order64, void* ws,
+               size_t ws_bytes, cudaStream_t st);
+int linear_launch(const float* A, int64_t rows, int64_t k, int64_t lda, const float* W,
+                  const float* bias, int64_t n, const float* R, int64_t ldr, float* C,
+                  int64_t ldc, int flags, int precision, cudaStream_t st);
+int linear_ldw_launch(const float* A, int64_t rows, int64_t k, int64_t lda, const float* W,
+                      int64_t ldw, const float* bias, int64_t n, const float* R, int64_t ldr,
+                      float* C, int64_t ldc, int flags, int precision, cudaStream_t st);
+// tcgen05 path (gemm_tc.cu); returns O4D_E_UNSUPPORTED when the shape cannot use it.
+int linear_tc_launch(const float* A, int64_t rows, int64_t k, int64_t lda, const float* W,
+                     const float* bias, int64_t n, const float* R, int64_t ldr, float* C,
+                     int64_t ldc, int flags, int precision, cudaStream_t st);
+
+struct PtBlockParams {
+    const float *w1, *b1, *wq, *wk, *wv, *wp1, *bp1, *wp2, *bp2, *wa1, *ba1, *wa2, *ba2, *w3, *b3;
+    static PtBlockParams from(const float* const* p) {
+        PtBlockParams r;
+        r.w1 = p[0]; r.b1 = p[1]; r.wq = p[2]; r.wk = p[3]; r.wv = p[4];
+        r.wp1 = p[5]; r.bp1 = p[6]; r.wp2 = p[7]; r.bp2 = p[8];
+        r.wa1 = p[9]; r.ba1 = p[10]; r.wa2 = p[11]; r.ba2 = p[12]; r.w3 = p[13]; r.b3 = p[14];
+        return r;
+    }
+};
+
+// Attention core shared by the encoder (self) and decoder (cross):
+//   out = x_res + W3 . attn(q, ktab, vtab, pos, pos2, nbr) + b3      (n rows, d channels)
+// q (n,d) already projected; ktab/vtab (m,d); nbr (n,k) int32.
+size_t attn_core_workspace_bytes(int64_t n, int d, int k);
+int attn_core_launch(const PtBlockParams& P, const float* q, const float* ktab, const float* vtab,
+                     const float* pos, int64_t ldpos, const float* pos2, int64_t ldpos2,
+                     const int32_t* nbr, int64_t n, int d, int k, const float* x_res, float* out,
+                     int precision, void* ws, size_t ws_bytes, cudaStream_t st);
+
+size_t pt_block_ws(int64_t n, int64_t m, int d, int k, bool self_mode);
+int pt_block_launch(const float* const* p, const float* x, int64_t n, int d, const float* pos,
+                    int64_t ldpos, const float* x2, int64_t m, int d2, int64_t ldx2, const float* pos2,
+                    int64_t ldpos2, int k, int precision, float* z, int64_t* knn_idx_out, void* ws,
+                    size_t ws_bytes, cudaStream_t st);
+size_t down_ws(int64_t n, int d_in, int d_out, int factor, int k);
+int down_launch(const float* const* p, const float* x, int64_t n, int d_in, const float* pos,
+                int64_t ldpos, int d_out, int factor, int k, int norm, int64_t start_idx, int precision,
+                float* z, float* pos_out, int64_t* fps_idx_out, void* ws, size_t ws_bytes,
+                cudaStream_t st);
+
+// misc elementwise / gather kernels (misc.cu)
+int posenc_launch(const float* q, int64_t n, int d_in, int n_freq, float* out, cudaStream_t st);
+int local_blend_launch(const int32_t* idx, const float* dist, const float* feat, int64_t ldfeat,
+                       int64_t n, int k, int e, float* out, int64_t ldout, cudaStream_t st);
+int gather_max_launch(const float* y, int64_t ldy, const int32_t* nbr, int64_t n_out, int k, int d,
+                      float* z, cudaStream_t st);
+int layernorm_relu_launch(float* y, int64_t rows, int d, const float* gamma, const float* beta,
+                          float eps, cudaStream_t st);
+int gather_rows_launch(const float* src, int64_t ldsrc, const int32_t* idx, int64_t n, int d,
+                       float* dst, int64_t lddst, cudaStream_t st);
+int col_mean_launch(const float* x, int64_t rows, int d, float* out, cudaStream_t st);
+int copy2d_launch(const float* src, int64_t ldsrc, int64_t rows, int cols, float* dst,
+                  int64_t lddst, cudaStream_t st);
+int fill_col_launch(float* dst, int64_t ld, int64_t rows, int col, float value, cudaStream_t st);
+int widen_idx_launch(const int32_t* in, int64_t count, int64_t* out, cudaStream_t st);
+
+}  // namespace o4d

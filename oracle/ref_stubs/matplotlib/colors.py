@@ -1,0 +1,1 @@
+# empty import stub (see README.md)

@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""Headline benchmark: implicit-decoder queries/sec on the GREATER-shape synthetic workload
+(BASELINE.json configs[1]: 14336 points, 12 frames, 524288 grid queries -> 534,528 query
+points, 6 MLP blocks, 2 cross-attention layers, implicit_batch_size 32768).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]           # this repo (CUDA, sm_100a)
+    python bench.py --impl reference ...                            # CPU arm (oracle port)
+    torchrun --nproc-per-node N bench.py --gpus N ...               # one rank per GPU
+
+A step = one pass of the decoder hot path over all query mini-batches of one frame with
+the scene encoding resident (the eval/inference.py:204-246 loop).  Weak scaling: every
+rank decodes one whole frame (frames are independent: eval/test.py:67 loops over them)
+and the ranks all-gather their (N_q, d_out) outputs over NCCL.
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, 'occlusions-4d_b200')):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = 'implicit_queries_per_sec'
+UNIT = 'queries/s'
+FLOP_PER_QUERY = 47.89e6     # SURVEY.md section 8d / BASELINE.md section 2 (G = 9)
+FAMILIES = ['dense_layer', 'knn', 'fps', 'attn_gather_softmax', 'misc', 'fused_attn_mlp']
+
+
+def workload_config(batch):
+    return {'workload': 'GREATER synthetic: n_points=14336, video_len=12, 524288 grid queries (534528 points), '
+                        'attention mode, 6 MLP blocks, 2 cross-attn layers (K=14), d_hidden=416, d_out=9, '
+                        'seeded random-init weights',
+            'implicit_batch_size': batch,
+            'l2': 'a 256 MiB buffer is overwritten before every timed step (L2 flush); per-step activations '
+                  'are > 1 GiB anyway',
+            'parallelism': 'one frame of queries per rank, NCCL all-gather of outputs'}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[5:9]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def golden_scene():
+    z = np.load(os.path.join(ROOT, 'tests', 'golden', 'c2_greater_seeded.npz'))
+    return torch.from_numpy(z['abstract']), torch.from_numpy(z['glob'])
+
+
+def cpu_reference_rate(sample, threads=None):
+    """Oracle port (torch CPU fp32) of the decoder on `sample` queries of the workload; returns
+    (queries/s, seconds, threads)."""
+    from oracle import o4d_oracle as orc
+    from tests import configs
+    cfg = configs.C2_GREATER
+    if threads:
+        torch.set_num_threads(threads)
+    _, dec = configs.build_modules(cfg)
+    sd = orc.cast_state(dec.state_dict(), torch.float32)
+    abstract, glob = golden_scene()
+    q = configs.synthetic_queries(cfg)
+    sel = torch.linspace(0, q.shape[0] - 1, sample).long()
+    q = q[sel]
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        orc.decoder_forward(sd, cfg['implicit_args'], q, abstract, glob, chunk=4096)
+        dt = time.perf_counter() - t0
+    return sample / dt, dt, torch.get_num_threads()
+
+
+def run_reference(args):
+    """CPU arm: the reference's algorithm (oracle port; the reference is Python and cannot travel
+    to the GPU box) on the host cores, each step a bounded sample of the same workload."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from oracle import o4d_oracle as orc
+    from tests import configs
+    cfg = configs.C2_GREATER
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    _, dec = configs.build_modules(cfg)
+    sd = orc.cast_state(dec.state_dict(), torch.float32)
+    abstract, glob = golden_scene()
+    q_all = configs.synthetic_queries(cfg)
+    # calibrate on 1024 queries, then size a step so that warmup+steps take about two minutes
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        orc.decoder_forward(sd, cfg['implicit_args'], q_all[:1024], abstract, glob, chunk=1024)
+        rate = 1024 / (time.perf_counter() - t0)
+    total = args.steps + args.warmup
+    sample = int(max(1024, min(q_all.shape[0], rate * 120.0 / total)))
+    sample = sample // 1024 * 1024
+    sel = torch.linspace(0, q_all.shape[0] - 1, sample).long()
+    q = q_all[sel]
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            orc.decoder_forward(sd, cfg['implicit_args'], q, abstract, glob, chunk=4096)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            orc.decoder_forward(sd, cfg['implicit_args'], q, abstract, glob, chunk=4096)
+        dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    desc = '%d of %d grid queries per step (evenly strided), decoder only, scene encoding resident' % (
+        sample, q_all.shape[0])
+    line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic', 'config': workload_config(args.batch),
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+                             'sample': desc},
+            'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+def run_o4d(args):
+    import torch.distributed as dist
+    import o4d
+    from o4d import _lib, ops, parallel
+    from tests import configs
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py needs a CUDA device for the o4d arm (there is no CPU fallback)')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    lib = _lib.lib()
+    cfg = configs.C2_GREATER
+    batch = args.batch
+    enc, dec = configs.build_modules(cfg, dev)
+    if args.precision is not None:
+        enc.o4d_precision = dec.o4d_precision = args.precision
+    precision = ops.default_precision() if args.precision is None else args.precision
+    pcl = configs.synthetic_cloud(cfg).to(dev)
+    # frame (time index) per rank: frames are the independent units sharded across GPUs
+    q_host = configs.synthetic_queries(cfg, time_idx=rank % cfg['video_len']).contiguous().pin_memory()
+    nq = q_host.shape[0]
+    q_dev = q_host.to(dev)
+    d_out = cfg['implicit_args']['d_out']
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    with torch.no_grad():
+        # ---- encoder: once per scene; timed on its own (pts/s), outside the query metric
+        for _ in range(max(1, args.warmup)):
+            abstract, glob, _ = enc(pcl[None], False)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        enc_iters = max(2, min(args.steps, 5))
+        for _ in range(enc_iters):
+            abstract, glob, _ = enc(pcl[None], False)
+        e1.record()
+        torch.cuda.synchronize()
+        enc_ms = e0.elapsed_time(e1) / enc_iters
+        abstract, glob = abstract[0].contiguous(), glob[0].contiguous()
+        scene = dec.o4d_scene(abstract, glob)
+        dcfg, dparams = dec.o4d_config(), dec.o4d_params()
+        out_dev = torch.empty((nq, d_out), dtype=torch.float32, device=dev)
+        gathered = torch.empty((world * nq, d_out), dtype=torch.float32, device=dev) if world > 1 else None
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+        def step_device():
+            flush.fill_(1)                                   # L2 flush (torch fill, not an o4d kernel)
+            for s in range(0, nq, batch):
+                ops.decoder_forward(dcfg, dparams, scene, q_dev[s:s + batch], want_penult=False,
+                                    out=out_dev[s:s + batch])
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, out_dev)
+
+        for _ in range(args.warmup):
+            step_device()
+        sampler = ClockSampler(local)
+        barrier()
+        if rank == 0:
+            sampler.start()
+        launches0 = lib.o4d_launch_count()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(args.steps):
+            step_device()
+        t1.record()
+        barrier()
+        launches = lib.o4d_launch_count() - launches0
+        clocks = sampler.stop() if rank == 0 else None
+        ms = max_over_ranks(t0.elapsed_time(t1))
+        value = world * nq * args.steps / (ms / 1e3)
+
+        # ---- end to end: HOST query buffer -> C-ABI host loop (H2D, forward, D2H per mini-batch)
+        out_host = torch.empty((nq, d_out), dtype=torch.float32).pin_memory()
+        ops.decoder_run_host(dcfg, dparams, scene, q_host, batch, out_host)
+        barrier()
+        w0 = time.perf_counter()
+        e2e_steps = max(1, min(args.steps, 3))
+        for _ in range(e2e_steps):
+            ops.decoder_run_host(dcfg, dparams, scene, q_host, batch, out_host)   # synchronises inside
+        barrier()
+        e2e_ms = max_over_ranks((time.perf_counter() - w0) * 1e3)
+        e2e_value = world * nq * e2e_steps / (e2e_ms / 1e3)
+        e2e_matches = bool(torch.equal(out_host, out_dev.cpu()))
+
+        # ---- roofline of the dominant kernel family: one extra profiled step right after
+        roofline, families = None, None
+        if rank == 0:
+            lib.o4d_profile_enable(1)
+            step_device()
+            torch.cuda.synchronize()
+            import ctypes
+            n = len(FAMILIES)
+            ms_a, fl_a, ct_a = (ctypes.c_double * n)(), (ctypes.c_double * n)(), (ctypes.c_int64 * n)()
+            lib.o4d_profile_read(n, ms_a, fl_a, ct_a)
+            lib.o4d_profile_enable(0)
+            families = {FAMILIES[i]: {'ms': ms_a[i], 'launches': ct_a[i], 'tflops': (fl_a[i] / ms_a[i] / 1e9) if ms_a[i] > 0 else 0.0}
+                        for i in range(n) if ct_a[i]}
+            top = max(families, key=lambda k: families[k]['ms'])
+            peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+            if os.path.isfile(peaks_path):
+                pk = json.load(open(peaks_path))
+                peak, which = float(pk['bf16_tflops_sustained']), 'MEASURED_PEAKS.json bf16_tflops_sustained'
+            else:
+                peak, which = 1400.0, 'fallback (B200_PROFILING.md sustained ~1.4 PFLOP/s)'
+            step_total = sum(f['ms'] for f in families.values())
+            ach = families[top]['tflops']
+            roofline = {'bound': 'tensor', 'kernel': top, 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s',
+                        'frac': ach / peak, 'traffic': None, 'peak_source': which,
+                        'share_of_step': families[top]['ms'] / step_total if step_total else None,
+                        'avg_launch_ms': families[top]['ms'] / families[top]['launches'],
+                        'measured': 'CUDA events around every launch of the family, one extra step after the timed region',
+                        'whole_step_algorithmic_tflops': FLOP_PER_QUERY * value / world / 1e12}
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, secs, threads = cpu_reference_rate(args.cpu_sample)
+        cpu_base = {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                    'sample': '%d of %d grid queries (evenly strided), decoder only, oracle port torch-CPU fp32, '
+                              '%.1f s' % (args.cpu_sample, nq, secs)}
+    if rank == 0:
+        line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+                'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+                'scaling': 'weak', 'vs_baseline': None, 'dtype': {0: 'f32', 1: 'bf16x3', 2: 'bf16'}[precision],
+                'data': 'synthetic', 'config': workload_config(batch), 'queries_per_step_per_gpu': nq,
+                'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': nq * 16,
+                        'd2h_bytes_per_step': nq * d_out * 4, 'steps': e2e_steps,
+                        'bit_identical_to_device_path': e2e_matches},
+                'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'kernel_families': families,
+                'cpu_baseline': cpu_base,
+                'encoder': {'pts_per_s': cfg['n_points'] / (enc_ms / 1e3), 'ms': enc_ms, 'n_points': cfg['n_points']},
+                'tcgen05': bool(lib.o4d_has_tcgen05())}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='o4d', choices=['o4d', 'reference'])
+    ap.add_argument('--batch', type=int, default=32768, help='implicit_batch_size')
+    ap.add_argument('--precision', type=int, default=None, help='0 fp32 CUDA cores, 1 tcgen05 bf16x3, 2 bf16')
+    ap.add_argument('--cpu-sample', type=int, default=16384)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_o4d(args)
+
+
+if __name__ == '__main__':
+    main()

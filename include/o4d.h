@@ -46,6 +46,16 @@ int o4d_abi_version(void);
 /* 1 when the library was built with the tcgen05 (tensor-core) GEMM path. */
 int o4d_has_tcgen05(void);
 
+/* Diagnostics (not on the data path).  o4d_launch_count: kernels this library has launched
+ * in the process so far.  o4d_profile_enable(1) makes every kernel family record CUDA
+ * events on its launching stream; o4d_profile_read sums elapsed ms / algorithmic flops /
+ * launch counts per family (0 dense layer, 1 kNN, 2 FPS, 3 attention gather+softmax,
+ * 4 misc, 5 fused attention MLP) and synchronises on the recorded events;
+ * o4d_profile_enable(0|1) also clears the records. */
+uint64_t o4d_launch_count(void);
+void o4d_profile_enable(int on);
+int o4d_profile_read(int n_families, double* ms_out, double* flops_out, int64_t* count_out);
+
 /* ------------------------------------------------------------------ kNN
  * Brute-force k nearest neighbours in 3-D, ascending (distance, index), distance =
  * fp32 ((dx*dx + dy*dy) + dz*dz) without FMA contraction.
@@ -88,6 +98,12 @@ int o4d_linear_f32(const float* A, int64_t rows, int64_t k, int64_t lda,
                    const float* R, int64_t ldr,
                    float* C, int64_t ldc, int flags, int precision, void* stream);
 
+/* ------------------------------------------------------------------ Fourier features
+ * positional_encode, model/implicit.py:20-43 with base_frequency 0.1 (:184,:405):
+ * points (n, d_in) -> out (n, d_in*(2*n_freq+1)) = [x, sin(w_0 x), cos(w_0 x), ...],
+ * w_p = 2*pi*0.1*2^p, accurate sinf/cosf. */
+int o4d_posenc_f32(const float* points, int64_t n, int d_in, int n_freq, float* out, void* stream);
+
 /* ------------------------------------------------------------------ vector attention
  * One PointTransformerBlock, model/modules.py:18-67 wrapping PointTransformerLayer,
  * model/point_transformer_layer.py:116-183:
@@ -110,6 +126,19 @@ int o4d_pt_block_forward(const float* const* p,
                          const float* pos2, int64_t ldpos2,
                          int k, int precision,
                          float* z, int64_t* knn_idx_out,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* Bare PointTransformerLayer.forward, model/point_transformer_layer.py:148-183 (what
+ * o4d_pt_block_forward wraps with layer1/layer3).  `p` = its 11 tensors in state_dict
+ * order: to_q.w, to_k.w, to_v.w, pos_mlp.0.{w,b}, pos_mlp.2.{w,b}, attn_mlp.0.{w,b},
+ * attn_mlp.2.{w,b}.  out (n, d).  Workspace: o4d_pt_block_workspace_bytes. */
+#define O4D_PTLAYER_NPARAMS 11
+int o4d_pt_layer_forward(const float* const* p,
+                         const float* x, int64_t n, int d, const float* pos, int64_t ldpos,
+                         const float* x2, int64_t m, int d2, int64_t ldx2,
+                         const float* pos2, int64_t ldpos2,
+                         int k, int precision,
+                         float* out, int64_t* knn_idx_out,
                          void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------ down transition

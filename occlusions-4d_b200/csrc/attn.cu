@@ -133,6 +133,7 @@ int attn_core_launch(const PtBlockParams& P, const float* q, const float* ktab, 
     float* a1 = a.get<float>((size_t)cq * k * d);
     float* hid = a.get<float>((size_t)cq * k * 2 * d);
     float* agg = a.get<float>((size_t)n * d);
+    if (P.w3 == nullptr) agg = out;  // bare PointTransformerLayer: no layer3 / residual
     if (!a.ok) {
         set_error("attention: workspace too small (%zu < %zu)", ws_bytes, a.off);
         return O4D_E_WORKSPACE;
@@ -147,15 +148,22 @@ int attn_core_launch(const PtBlockParams& P, const float* q, const float* ktab, 
         const int64_t rows = nq * k;
         int64_t blocks = cdiv(rows, 8);
         if (blocks > 148 * 8) blocks = 148 * 8;
-        attn_prep_kernel<<<(unsigned)blocks, 256, smem, st>>>(q, ktab, pos, ldpos, pos2, ldpos2, nbr, i0, rows, d, k,
-                                                              P.wp1, P.bp1, P.wp2, P.bp2, delta, a1);
-        O4D_LAUNCH_CHECK();
+        {
+            ProfScope prof(PROF_ATTN_GLUE, 2.0 * (double)rows * (3 + d) * POS_HID, st);
+            attn_prep_kernel<<<(unsigned)blocks, 256, smem, st>>>(q, ktab, pos, ldpos, pos2, ldpos2, nbr, i0, rows, d,
+                                                                  k, P.wp1, P.bp1, P.wp2, P.bp2, delta, a1);
+            O4D_LAUNCH_CHECK();
+        }
         O4D_TRY(linear_launch(a1, rows, d, d, P.wa1, P.ba1, 2 * d, nullptr, 0, hid, 2 * d, O4D_RELU_OUT, precision, st));
         O4D_TRY(linear_launch(hid, rows, 2 * d, 2 * d, P.wa2, P.ba2, d, nullptr, 0, a1, d, 0, precision, st));
-        attn_softmax_agg_kernel<O4D_MAX_K><<<(unsigned)cdiv(nq * d, 256), 256, 0, st>>>(
-            a1, delta, vtab, nbr, i0, nq, d, k, inv_sqrt_d, agg);
-        O4D_LAUNCH_CHECK();
+        {
+            ProfScope prof(PROF_ATTN_GLUE, 6.0 * (double)rows * d, st);
+            attn_softmax_agg_kernel<O4D_MAX_K><<<(unsigned)cdiv(nq * d, 256), 256, 0, st>>>(
+                a1, delta, vtab, nbr, i0, nq, d, k, inv_sqrt_d, agg);
+            O4D_LAUNCH_CHECK();
+        }
     }
+    if (P.w3 == nullptr) return 0;
     // z = x + W3 agg + b3   (modules.py:64-65)
     O4D_TRY(linear_launch(agg, n, d, d, P.w3, P.b3, d, x_res, d, out, d, 0, precision, st));
     return 0;
@@ -205,7 +213,51 @@ int pt_block_launch(const float* const* p, const float* x, int64_t n, int d, con
                             (char*)ws + a.off, ws_bytes - a.off, st);
 }
 
+// Bare PointTransformerLayer.forward (point_transformer_layer.py:148-183): no layer1/layer3.
+int pt_layer_launch(const float* const* p, const float* x, int64_t n, int d, const float* pos,
+                    int64_t ldpos, const float* x2, int64_t m, int d2, int64_t ldx2, const float* pos2,
+                    int64_t ldpos2, int k, int precision, float* out, int64_t* knn_idx_out, void* ws,
+                    size_t ws_bytes, cudaStream_t st) {
+    O4D_REQUIRE(p && x && pos && out, "pt_layer: null pointer");
+    const bool self_mode = (x2 == nullptr);
+    if (self_mode) {
+        m = n; d2 = d; pos2 = pos; ldpos2 = ldpos; x2 = x; ldx2 = d;
+    } else {
+        O4D_REQUIRE(pos2 && m >= 1 && d2 >= 1 && ldx2 >= d2, "pt_layer: bad cross-attention inputs");
+    }
+    O4D_REQUIRE(k <= m, "pt_layer: k=%d exceeds the number of key points %lld", k, (long long)m);
+    PtBlockParams P;
+    P.w1 = P.b1 = P.w3 = P.b3 = nullptr;
+    P.wq = p[0]; P.wk = p[1]; P.wv = p[2]; P.wp1 = p[3]; P.bp1 = p[4]; P.wp2 = p[5]; P.bp2 = p[6];
+    P.wa1 = p[7]; P.ba1 = p[8]; P.wa2 = p[9]; P.ba2 = p[10];
+    Arena a(ws, ws_bytes);
+    a.get<float>((size_t)n * d);  // (slot kept so the layout matches pt_block_ws)
+    float* q = a.get<float>((size_t)n * d);
+    float* ktab = a.get<float>((size_t)m * d);
+    float* vtab = a.get<float>((size_t)m * d);
+    int32_t* nbr = a.get<int32_t>((size_t)n * k);
+    if (!a.ok) {
+        set_error("pt_layer: workspace too small (%zu)", ws_bytes);
+        return O4D_E_WORKSPACE;
+    }
+    O4D_TRY(linear_launch(x, n, d, d, P.wq, nullptr, d, nullptr, 0, q, d, 0, precision, st));
+    O4D_TRY(linear_launch(x2, m, d2, ldx2, P.wk, nullptr, d, nullptr, 0, ktab, d, 0, precision, st));
+    O4D_TRY(linear_launch(x2, m, d2, ldx2, P.wv, nullptr, d, nullptr, 0, vtab, d, 0, precision, st));
+    O4D_TRY(knn_launch(pos, n, ldpos, pos2, m, ldpos2, k, 0, nbr, knn_idx_out, nullptr, st));
+    return attn_core_launch(P, q, ktab, vtab, pos, ldpos, pos2, ldpos2, nbr, n, d, k, nullptr, out, precision,
+                            (char*)ws + a.off, ws_bytes - a.off, st);
+}
+
 }  // namespace o4d
+
+extern "C" int o4d_pt_layer_forward(const float* const* p, const float* x, int64_t n, int d,
+                                    const float* pos, int64_t ldpos, const float* x2, int64_t m, int d2,
+                                    int64_t ldx2, const float* pos2, int64_t ldpos2, int k, int precision,
+                                    float* out, int64_t* knn_idx_out, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+    return o4d::pt_layer_launch(p, x, n, d, pos, ldpos, x2, m, d2, ldx2, pos2, ldpos2, k, precision, out,
+                                knn_idx_out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
 
 extern "C" size_t o4d_pt_block_workspace_bytes(int64_t n, int64_t m, int d, int d2, int k) {
     (void)d2;

@@ -261,6 +261,7 @@ int fps_launch(const float* xyz, int64_t n, int64_t ld, int64_t n_out, int64_t s
         set_error("fps: workspace too small (%zu < %zu)", ws_bytes, fps_ws_bytes(n));
         return O4D_E_WORKSPACE;
     }
+    ProfScope prof(PROF_FPS, 10.0 * (double)n * (double)n_out, st);
     int32_t* counts = (int32_t*)ws;
     float* mind = (float*)((char*)ws + align_up((size_t)n * sizeof(int32_t), 256));
     O4D_CUDA(cudaMemsetAsync(counts, 0, (size_t)n * sizeof(int32_t), st));

@@ -125,6 +125,7 @@ int linear_ldw_launch(const float* A, int64_t rows, int64_t k, int64_t lda, cons
                 (long long)rows, (long long)k, (long long)n);
     O4D_REQUIRE(lda >= k && ldw >= k && ldc >= n && (!R || ldr >= n), "linear: bad leading dimension");
     O4D_REQUIRE(precision >= 0 && precision <= 2, "linear: precision %d not in {0,1,2}", precision);
+    ProfScope prof(PROF_LINEAR, 2.0 * (double)rows * (double)k * (double)n, st);
     if (precision != 0 && ldw == k) {
         int rc = linear_tc_launch(A, rows, k, lda, W, bias, n, R, ldr, C, ldc, flags, precision, st);
         if (rc != O4D_E_UNSUPPORTED) return rc;

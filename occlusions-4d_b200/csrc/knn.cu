@@ -158,6 +158,7 @@ int knn_launch(const float* query, int64_t nq, int64_t ldq, const float* ref, in
                 (long long)m, k);
     O4D_REQUIRE(nq >= 0, "knn: negative query count");
     if (nq == 0) return 0;
+    ProfScope prof(PROF_KNN, 8.0 * (double)nq * (double)m, st);
     // enough threads to cover the machine (148 SMs x 2048 resident threads) a few times.
     int S = 1;
     if (nq * 1 < 600000 && m >= 128) S = 4;

@@ -222,3 +222,8 @@ int widen_idx_launch(const int32_t* in, int64_t count, int64_t* out, cudaStream_
 }
 
 }  // namespace o4d
+
+extern "C" int o4d_posenc_f32(const float* points, int64_t n, int d_in, int n_freq, float* out, void* stream) {
+    O4D_REQUIRE(points && out && n >= 0 && d_in >= 1, "o4d_posenc_f32: bad argument");
+    return o4d::posenc_launch(points, n, d_in, n_freq, out, (cudaStream_t)stream);
+}

@@ -28,8 +28,20 @@ void set_error(const char* fmt, ...);
         }                                                                           \
     } while (0)
 
+void count_launch();  // diagnostics: kernels launched by this library (o4d_launch_count)
+
+// Opt-in kernel-family timer (o4d_profile_enable): CUDA events on the launching stream.
+enum { PROF_LINEAR = 0, PROF_KNN = 1, PROF_FPS = 2, PROF_ATTN_GLUE = 3, PROF_MISC = 4, PROF_FUSED = 5 };
+struct ProfScope {
+    ProfScope(int family, double flops, cudaStream_t st);
+    ~ProfScope();
+    int rec_;
+    cudaStream_t st_;
+};
+
 #define O4D_LAUNCH_CHECK()                                                          \
     do {                                                                            \
+        ::o4d::count_launch();                                                      \
         cudaError_t e__ = cudaGetLastError();                                       \
         if (e__ != cudaSuccess) {                                                   \
             ::o4d::set_error("kernel launch failed: %s (%s:%d)",                    \

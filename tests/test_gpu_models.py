@@ -1,0 +1,228 @@
+"""GPU parity tests of the encoder / decoder modules (nn.Module API -> C ABI -> CUDA)
+against the reference's golden vectors and the CPU oracle, plus size-independent
+properties at BASELINE.json's full sizes.
+
+Tolerance (north star): outputs within 1e-3 of the fp32 reference, measured as
+max|ours - ref| / max|ref| per tensor (logits reach O(100), so element-wise relative error
+near zero crossings is meaningless); kNN / FPS indices bit-exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import o4d
+from o4d import ops, parallel
+from oracle import o4d_oracle as orc
+from tests import configs
+from tests.test_oracle import GOLD, boundary_tie_free, load, relerr, split_state
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+TOL = 1e-3          # the north-star bar
+TOL_TIGHT = 1e-4    # what the fp32 / bf16x3 paths actually deliver
+
+
+def modules_from_golden(cfg, g):
+    enc, dec = configs.build_modules(cfg)
+    if any(k.startswith('enc.') for k in g):
+        sd_e, sd_d = split_state(g)
+        enc.load_state_dict(sd_e, strict=True)
+        dec.load_state_dict(sd_d, strict=True)
+    else:
+        assert np.allclose(configs.weight_checksum(enc), g['enc_checksum'], rtol=0, atol=1e-9)
+        assert np.allclose(configs.weight_checksum(dec), g['dec_checksum'], rtol=0, atol=1e-9)
+    return enc.to(DEV).eval(), dec.to(DEV).eval()
+
+
+CASES = [('tiny_greater.npz', configs.TINY_GREATER), ('tiny_carla.npz', configs.TINY_CARLA),
+         ('c1_greater_seeded.npz', configs.C1_GREATER), ('c2_greater_seeded.npz', configs.C2_GREATER),
+         ('c3_carla_seeded.npz', configs.C3_CARLA)]
+
+
+@pytest.mark.parametrize('name,cfg', CASES, ids=[c[0][:-4] for c in CASES])
+def test_encoder_and_decoder_match_reference_golden(name, cfg):
+    g = load(name)
+    enc, dec = modules_from_golden(cfg, g)
+    with torch.no_grad():
+        abstract, glob, coords = enc(g['pcl'].to(DEV)[None], True)
+    assert abstract.shape == (1,) + tuple(g['abstract'].shape) and glob.shape == (1,) + tuple(g['glob'].shape)
+    # FPS picks are bit-exact at every level (coords after each down transition)
+    for l in range(1, cfg['pcl_args']['down_blocks'] + 1):
+        assert torch.equal(coords[1 + 2 * l].cpu()[0], g['level_pos_%d' % l]), 'level %d coordinates' % l
+    assert torch.equal(abstract.cpu()[0][:, :3], g['abstract'][:, :3])
+    e_abs, e_glob = relerr(abstract.cpu()[0], g['abstract']), relerr(glob.cpu()[0], g['glob'])
+    assert e_abs < TOL_TIGHT and e_glob < TOL_TIGHT, (e_abs, e_glob)
+    # decoder on the REFERENCE's abstract cloud (isolates it from encoder rounding)
+    with torch.no_grad():
+        out, pen = dec(g['query'].to(DEV), g['abstract'].to(DEV), g['glob'].to(DEV), None)
+    ok = boundary_tie_free(g['query'][:, :3], g['abstract'][:, :3],
+                           [cfg['implicit_args']['num_local_features'], cfg['implicit_args']['cross_attn_neighbors']])
+    if cfg['pcl_args']['abstract_levels'] == 1:
+        assert bool(ok.all())
+    assert ok.float().mean() > 0.5
+    e_out, e_pen = relerr(out.cpu()[ok], g['out'][ok]), relerr(pen.cpu()[ok][:, :16], g['penult'][ok])
+    assert e_out < TOL_TIGHT and e_pen < TOL_TIGHT, (e_out, e_pen)
+    # end to end (our encoder feeding our decoder) stays inside the north-star bar
+    with torch.no_grad():
+        out2, _ = dec(g['query'].to(DEV), abstract[0], glob[0], None)
+    assert relerr(out2.cpu()[ok], g['out'][ok]) < TOL
+
+
+def test_tie_rows_match_the_oracle_canonical_rule():
+    """Duplicate abstract positions (abstract_levels=2): the reference's topk leaves the choice
+    open; we must agree with the oracle's (distance, index) rule on EVERY row."""
+    g = load('tiny_carla.npz')
+    cfg = configs.TINY_CARLA
+    _, dec = modules_from_golden(cfg, g)
+    _, sd_d = split_state(g)
+    want, _ = orc.decoder_forward(sd_d, cfg['implicit_args'], g['query'], g['abstract'], g['glob'])
+    with torch.no_grad():
+        out, _ = dec(g['query'].to(DEV), g['abstract'].to(DEV), g['glob'].to(DEV), None)
+    assert relerr(out.cpu(), want) < TOL_TIGHT
+
+
+def test_call_forms_of_both_reference_callers():
+    g = load('tiny_greater.npz')
+    enc, dec = modules_from_golden(configs.TINY_GREATER, g)
+    pcl = g['pcl'].to(DEV)[None]
+    with torch.no_grad():
+        r3 = enc(pcl, False)                 # eval/inference.py:195
+        r4 = enc(pcl, False, False)          # pipeline.py:93-94
+        assert len(r3) == 3 and len(r4) == 4 and r3[2] is None and r4[3] is None
+        assert torch.equal(r3[0], r4[0])
+        q = g['query'].to(DEV)
+        o2 = dec(q, r3[0][0], r3[1][0], None)                    # inference.py:211 (unbatched)
+        o3 = dec(q[None], r3[0], r3[1], None, False)             # pipeline.py:193 (batched, extra flag)
+        assert len(o2) == 2 and len(o3) == 3 and o3[2] is None
+        assert o2[0].shape == (q.shape[0], 5) and o3[0].shape == (1, q.shape[0], 5)
+        assert torch.equal(o2[0], o3[0][0])
+        # separated coordinates / features (implicit.py:286-290 else-branch)
+        o4 = dec(q, r3[0][0][:, :3], r3[1][0], r3[0][0][:, 3:])
+        assert torch.equal(o4[0], o2[0])
+        # the caller post-processes in place (inference.py:218): result must be writable
+        o2[0][..., 0] = torch.sigmoid(o2[0][..., 0])
+        with pytest.raises(AssertionError):
+            dec(q[None].expand(2, -1, -1), r3[0].expand(2, -1, -1), r3[1].expand(2, -1), None)  # B must be 1
+
+
+def test_batched_encoder_equals_per_cloud():
+    g = load('tiny_greater.npz')
+    enc, _ = modules_from_golden(configs.TINY_GREATER, g)
+    other = configs.synthetic_cloud(dict(configs.TINY_GREATER, seed=99))
+    both = torch.stack([g['pcl'], other]).to(DEV)
+    with torch.no_grad():
+        a, gl, _ = enc(both, False)
+        a0, g0, _ = enc(both[:1], False)
+        a1, g1, _ = enc(both[1:], False)
+    assert torch.equal(a[0], a0[0]) and torch.equal(a[1], a1[0]) and torch.equal(gl[1], g1[0])
+
+
+def test_zero_padded_cloud_runs_and_matches_oracle():
+    cfg = configs.TINY_GREATER
+    g = load('tiny_greater.npz')
+    enc, _ = modules_from_golden(cfg, g)
+    pcl = configs.synthetic_cloud(cfg, duplicates=100)      # geometry.py:320-322 style padding
+    sd_e, _ = split_state(g)
+    want, want_g = orc.encoder_forward(sd_e, cfg['pcl_args'], pcl)
+    with torch.no_grad():
+        a, gl, _ = enc(pcl.to(DEV)[None], False)
+    assert torch.equal(a.cpu()[0][:, :3], want[:, :3])
+    assert relerr(a.cpu()[0], want) < TOL_TIGHT and relerr(gl.cpu()[0], want_g) < TOL_TIGHT
+
+
+def test_random_fps_start_is_used_in_training_configuration():
+    cfg = dict(configs.TINY_GREATER)
+    cfg['pcl_args'] = dict(cfg['pcl_args'], fps_random_start=True)
+    enc, _ = configs.build_modules(cfg)
+    enc = enc.to(DEV).eval()
+    pcl = configs.synthetic_cloud(cfg).to(DEV)[None]
+    with torch.no_grad():
+        torch.manual_seed(1)
+        a = enc(pcl, False)[0]
+        torch.manual_seed(2)
+        b = enc(pcl, False)[0]
+        torch.manual_seed(1)
+        c = enc(pcl, False)[0]
+    assert torch.equal(a, c) and not torch.equal(a[..., :3], b[..., :3])
+
+
+# ------------------------------------------------------------ full-size properties (config 2)
+
+@pytest.fixture(scope='module')
+def c2():
+    g = load('c2_greater_seeded.npz')
+    enc, dec = modules_from_golden(configs.C2_GREATER, g)
+    return g, enc, dec
+
+
+def test_full_size_minibatch_invariance_and_host_loop(c2):
+    """524,288-query grid (534,528 points): per-query results must not depend on how the
+    frame is cut into mini-batches, and the host-buffer C-ABI loop must equal the module."""
+    g, enc, dec = c2
+    cfg = configs.C2_GREATER
+    q = configs.synthetic_queries(cfg)
+    assert q.shape[0] == 534528
+    abstract, glob = g['abstract'].to(DEV), g['glob'].to(DEV)
+    qd = q.to(DEV)
+    with torch.no_grad():
+        full = torch.cat([dec(qd[s:s + 32768], abstract, glob, None)[0] for s in range(0, q.shape[0], 32768)])
+        sel = torch.linspace(0, q.shape[0] - 1, 4096).long()
+        # golden subset of the reference
+        assert relerr(full[sel.to(DEV)].cpu(), g['out']) < 1e-4
+        # different mini-batch size -> same answers
+        odd = torch.cat([dec(qd[s:s + 8192], abstract, glob, None)[0] for s in range(0, 65536, 8192)])
+        assert relerr(odd.cpu(), full[:65536].cpu()) < 1e-6
+        # host-buffer loop through the C ABI (what bench.py's e2e leg times)
+        scene = dec.o4d_scene(abstract, glob)
+        host = ops.decoder_run_host(dec.o4d_config(), dec.o4d_params(), scene, q[:100000].contiguous(), 32768)
+    assert torch.equal(host, full[:100000].cpu())
+    assert bool(torch.isfinite(full).all())
+
+
+def test_full_size_sharded_decode_single_process(c2):
+    g, enc, dec = c2
+    q = configs.synthetic_queries(configs.C2_GREATER)[:70000].to(DEV)
+    abstract, glob = g['abstract'].to(DEV), g['glob'].to(DEV)
+    with torch.no_grad():
+        fn = lambda b: dec(b, abstract, glob, None)[0]
+        whole = parallel.decode_sharded(fn, q, 32768)
+        parts = []
+        for r in range(3):   # emulate three ranks' contiguous shards
+            a, b = parallel.shard_range(q.shape[0], r, 3)
+            parts.append(torch.cat([fn(q[s:min(s + 32768, b)]) for s in range(a, b, 32768)]))
+    assert relerr(torch.cat(parts).cpu(), whole.cpu()) < 1e-6
+
+
+def test_full_size_encoder_is_deterministic(c2):
+    g, enc, dec = c2
+    pcl = g['pcl'].to(DEV)[None]
+    with torch.no_grad():
+        a1, g1, _ = enc(pcl, False)
+        a2, g2, _ = enc(pcl, False)
+    assert torch.equal(a1, a2) and torch.equal(g1, g2)
+    assert a1.shape == (1, 531, 291)
+
+
+# ------------------------------------------------------------ released checkpoints (optional)
+
+@pytest.mark.parametrize('which', ['greater', 'carla'])
+def test_released_checkpoint_parity(which):
+    path = os.path.join(GOLD, '_ckpt', which + '_nets.pt')
+    if not os.path.isfile(path):
+        pytest.skip('checkpoint fixture not generated (tests/golden/make_golden.py --ckpt)')
+    ck = torch.load(path, map_location='cpu', weights_only=True)
+    enc = o4d.PointCompletionNetV3(**ck['pcl_args'])
+    dec = o4d.LocalPclResnetFC(**ck['implicit_args'])
+    enc.load_state_dict(ck['pcl_net'], strict=True)
+    dec.load_state_dict(ck['implicit_net'], strict=True)
+    enc, dec = enc.to(DEV).eval(), dec.to(DEV).eval()
+    with torch.no_grad():
+        a, gl, _ = enc(ck['pcl'].to(DEV)[None], False)
+        out, pen = dec(ck['query'].to(DEV), ck['abstract'].to(DEV), ck['glob'].to(DEV), None)
+    assert torch.equal(a.cpu()[0][:, :3], ck['abstract'][:, :3])
+    assert relerr(a.cpu()[0], ck['abstract']) < TOL and relerr(gl.cpu()[0], ck['glob']) < TOL
+    ok = boundary_tie_free(ck['query'][:, :3], ck['abstract'][:, :3],
+                           [ck['implicit_args']['num_local_features'], ck['implicit_args']['cross_attn_neighbors']])
+    assert relerr(out.cpu()[ok], ck['out'][ok]) < TOL
+    assert relerr(pen.cpu()[ok][:, :16], ck['penult'][ok]) < TOL

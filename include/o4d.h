@@ -87,7 +87,7 @@ int o4d_fps_f32(const float* xyz, int64_t n, int64_t ld, int64_t n_out, int64_t 
 /* ------------------------------------------------------------------ dense layer
  * C = post( pre(A) @ W^T + bias ) [+ R],  replaces every torch.nn.Linear on the path
  * (cuBLAS SGEMM in the reference).  A (rows, k) lda; W (n, k) row-major exactly as
- * nn.Linear stores it; bias (n) or NULL; R (rows, n) ldr or NULL (may alias C);
+ * nn.Linear stores it; bias (n) or NULL; R (rows, n) ldr or NULL (may alias C; A must NOT alias C);
  * flags: O4D_RELU_IN applies ReLU to A on load, O4D_RELU_OUT to the result before R.
  * precision: 0 = fp32 CUDA-core FMA, 1 = tcgen05 bf16x3 split (fp32-grade), 2 = tcgen05
  * single bf16 (fast, ~3e-3).  */

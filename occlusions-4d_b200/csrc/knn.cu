@@ -150,6 +150,10 @@ static int knn_dispatch_s(int S, dim3 grid_unused, const float* query, int64_t n
 int knn_launch(const float* query, int64_t nq, int64_t ldq, const float* ref, int64_t m,
                int64_t ldr, int k, int sqrt_dist, int32_t* idx32, int64_t* idx64, float* dist,
                cudaStream_t st) {
+    O4D_REQUIRE(nq >= 0, "knn: negative query count");
+    O4D_REQUIRE(k >= 1 && k <= O4D_MAX_K, "knn: k=%d outside [1,%d]", k, O4D_MAX_K);
+    O4D_REQUIRE(m >= k, "knn: need k <= m (m=%lld, k=%d)", (long long)m, k);
+    if (nq == 0) return 0;
     O4D_REQUIRE(query && ref, "knn: null input");
     O4D_REQUIRE(idx32 || idx64 || dist, "knn: no output requested");
     O4D_REQUIRE(ldq >= 3 && ldr >= 3, "knn: leading dimensions must be >= 3");

@@ -139,9 +139,11 @@ def test_linear_strided_views_and_inplace_residual():
         got = ops.linear(base.to(DEV)[:, 3:], w.to(DEV), precision=prec)     # ld 291, offset 3 view
         assert relerr(got.cpu().double(), want) < (TOL_FP32 if prec == 0 else TOL_SPLIT)
         x = torch.randn(500, 416, generator=g).to(DEV)
+        h = torch.randn(500, 416, generator=g).to(DEV)
         w2 = (torch.randn(416, 416, generator=g) / 20.0).to(DEV)
-        ref = x.cpu().double() + torch.relu(x.cpu().double()) @ w2.cpu().double().t()
-        out = ops.linear(x, w2, residual=x, relu_in=True, precision=prec, out=x)   # R aliases C
+        ref = x.cpu().double() + torch.relu(h.cpu().double()) @ w2.cpu().double().t()
+        # x += W relu(h): R aliases C (allowed); A must not alias C (other tiles still read it)
+        out = ops.linear(h, w2, residual=x, relu_in=True, precision=prec, out=x)
         assert out.data_ptr() == x.data_ptr()
         assert relerr(out.cpu().double(), ref) < (TOL_FP32 if prec == 0 else TOL_SPLIT)
 

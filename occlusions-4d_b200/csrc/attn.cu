@@ -154,8 +154,8 @@ int attn_core_launch(const PtBlockParams& P, const float* q, const float* ktab, 
                                                                   k, P.wp1, P.bp1, P.wp2, P.bp2, delta, a1);
             O4D_LAUNCH_CHECK();
         }
-        O4D_TRY(linear_launch(a1, rows, d, d, P.wa1, P.ba1, 2 * d, nullptr, 0, hid, 2 * d, O4D_RELU_OUT, precision, st));
-        O4D_TRY(linear_launch(hid, rows, 2 * d, 2 * d, P.wa2, P.ba2, d, nullptr, 0, a1, d, 0, precision, st));
+        O4D_TRY(linear_ps_launch(P.ps, a1, rows, d, d, P.wa1, d, P.ba1, 2 * d, nullptr, 0, hid, 2 * d, O4D_RELU_OUT, precision, st));
+        O4D_TRY(linear_ps_launch(P.ps, hid, rows, 2 * d, 2 * d, P.wa2, 2 * d, P.ba2, d, nullptr, 0, a1, d, 0, precision, st));
         {
             ProfScope prof(PROF_ATTN_GLUE, 6.0 * (double)rows * d, st);
             attn_softmax_agg_kernel<O4D_MAX_K><<<(unsigned)cdiv(nq * d, 256), 256, 0, st>>>(
@@ -165,7 +165,7 @@ int attn_core_launch(const PtBlockParams& P, const float* q, const float* ktab, 
     }
     if (P.w3 == nullptr) return 0;
     // z = x + W3 agg + b3   (modules.py:64-65)
-    O4D_TRY(linear_launch(agg, n, d, d, P.w3, P.b3, d, x_res, d, out, d, 0, precision, st));
+    O4D_TRY(linear_ps_launch(P.ps, agg, n, d, d, P.w3, d, P.b3, d, x_res, d, out, d, 0, precision, st));
     return 0;
 }
 

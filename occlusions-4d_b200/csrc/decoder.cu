@@ -53,8 +53,11 @@ struct SceneView {
     float* zg;        // (n_blocks, H)   W_z[:, :Dg] g + b_z
     float* ktab[O4D_MAX_BLOCKS];  // (m, H) per cross layer
     float* vtab[O4D_MAX_BLOCKS];
+    size_t pack_off;  // byte offset of the pre-packed tcgen05 weights (precision != 0)
     size_t bytes;
 };
+
+static size_t packed_total_bytes(const o4d_decoder_config* c);
 
 static SceneView scene_view(const o4d_decoder_config* c, int64_t m, void* base) {
     Arena a(base ? base : nullptr, base ? (size_t)-1 : 0);
@@ -66,8 +69,49 @@ static SceneView scene_view(const o4d_decoder_config* c, int64_t m, void* base) 
         s.ktab[j] = a.get<float>((size_t)m * c->d_hidden);
         s.vtab[j] = a.get<float>((size_t)m * c->d_hidden);
     }
+    s.pack_off = a.off;
+    a.get<char>(packed_total_bytes(c));
     s.bytes = a.off;
     return s;
+}
+
+// Weights the tcgen05 path consumes, in a fixed order: sizing, packing (prepare) and lookup
+// (forward) all walk this list.  fn(weight, n, k, ldw).
+template <typename F>
+static void for_each_tc_weight(const o4d_decoder_config* c, const DecParams& d, F fn) {
+    const int H = c->d_hidden, E = c->d_latent_local, Dg = c->d_latent - c->d_latent_local;
+    const int pe_w = c->pos_encoding_freqs > 0 ? c->d_in * (2 * c->pos_encoding_freqs + 1) : c->d_in;
+    fn(d.lin_in_w, H, pe_w, pe_w);
+    for (int b = 0; b < c->n_blocks; ++b) {
+        fn(d.z_w[b] ? d.z_w[b] + Dg : nullptr, H, E, c->d_latent);  // local half of lin_z (column slice)
+        fn(d.fc0_w[b], H, H, H);
+        fn(d.fc1_w[b], H, H, H);
+    }
+    for (int j = 0; j < c->cross_attn_layers; ++j) {
+        const float* const* p = d.pt[j];
+        fn(p ? p[0] : nullptr, H, H, H);           // layer1
+        fn(p ? p[2] : nullptr, H, H, H);           // to_q
+        fn(p ? p[9] : nullptr, 2 * H, H, H);       // attn_mlp.0
+        fn(p ? p[11] : nullptr, H, 2 * H, 2 * H);  // attn_mlp.2
+        fn(p ? p[13] : nullptr, H, H, H);          // layer3
+    }
+}
+
+static size_t packed_total_bytes(const o4d_decoder_config* c) {
+    if (c->precision == 0) return 0;
+    DecParams d = {};
+    size_t total = 0;
+    for_each_tc_weight(c, d, [&](const float*, int n, int k, int) { total += align_up(tc_pack_bytes(n, k), 256); });
+    return total;
+}
+
+static void packed_set(const o4d_decoder_config* c, const DecParams& d, const void* scene, size_t pack_off, PackedSet* ps) {
+    if (c->precision == 0) return;
+    const char* p = (const char*)scene + pack_off;
+    for_each_tc_weight(c, d, [&](const float* w, int n, int k, int) {
+        ps->add(w, p);
+        p += align_up(tc_pack_bytes(n, k), 256);
+    });
 }
 
 int decoder_prepare(const o4d_decoder_config* c, const float* const* P, const float* pcl_abstract, int64_t m,
@@ -95,6 +139,16 @@ int decoder_prepare(const o4d_decoder_config* c, const float* const* P, const fl
         PtBlockParams pp = PtBlockParams::from(d.pt[j]);
         O4D_TRY(linear_launch(s.abs_feat, m, E, E, pp.wk, nullptr, H, nullptr, 0, s.ktab[j], H, 0, 0, st));
         O4D_TRY(linear_launch(s.abs_feat, m, E, E, pp.wv, nullptr, H, nullptr, 0, s.vtab[j], H, 0, 0, st));
+    }
+    if (c->precision != 0) {
+        // bf16 hi/lo shared-memory images of every weight the tcgen05 path reads
+        char* p = (char*)scene + s.pack_off;
+        int rc = 0;
+        for_each_tc_weight(c, d, [&](const float* w, int n, int k, int ldw) {
+            if (rc == 0) rc = tc_pack_launch(w, n, k, ldw, p, st);
+            p += align_up(tc_pack_bytes(n, k), 256);
+        });
+        O4D_TRY(rc);
     }
     return 0;
 }
@@ -145,6 +199,8 @@ int decoder_forward(const o4d_decoder_config* c, const float* const* P, const vo
     }
     DecParams d;
     dec_unpack(c, P, &d);
+    PackedSet ps;
+    packed_set(c, d, scene, s.pack_off, &ps);
 
     // implicit.py:328-339  K_l nearest abstract points, inverse-distance blend of their features
     O4D_TRY(knn_launch(query, nq, c->d_in, s.abs_xyz, m, 3, c->num_local_features, 1, w.idx_l, nullptr, w.dist_l, st));
@@ -155,23 +211,24 @@ int decoder_forward(const o4d_decoder_config* c, const float* const* P, const vo
     // implicit.py:403-408
     if (c->pos_encoding_freqs > 0) {
         O4D_TRY(posenc_launch(query, nq, c->d_in, c->pos_encoding_freqs, w.pe, st));
-        O4D_TRY(linear_launch(w.pe, nq, pe_w, pe_w, d.lin_in_w, d.lin_in_b, H, nullptr, 0, w.x, H, 0, prec, st));
+        O4D_TRY(linear_ps_launch(&ps, w.pe, nq, pe_w, pe_w, d.lin_in_w, pe_w, d.lin_in_b, H, nullptr, 0, w.x, H, 0, prec, st));
     } else {
-        O4D_TRY(linear_launch(query, nq, c->d_in, c->d_in, d.lin_in_w, d.lin_in_b, H, nullptr, 0, w.x, H, 0, prec, st));
+        O4D_TRY(linear_ps_launch(&ps, query, nq, c->d_in, c->d_in, d.lin_in_w, c->d_in, d.lin_in_b, H, nullptr, 0, w.x, H, 0, prec, st));
     }
     for (int b = 0; b < c->n_blocks; ++b) {
         // implicit.py:416-418  x += lin_z(features_query)   (global half pre-reduced into zg)
-        O4D_TRY(linear_ldw_launch(w.f_loc, nq, E, E, d.z_w[b] + Dg, c->d_latent, s.zg + (size_t)b * H, H, w.x, H,
-                                  w.x, H, 0, prec, st));
+        O4D_TRY(linear_ps_launch(&ps, w.f_loc, nq, E, E, d.z_w[b] + Dg, c->d_latent, s.zg + (size_t)b * H, H, w.x, H,
+                                 w.x, H, 0, prec, st));
         // implicit.py:93-101  x += fc_1(relu(fc_0(relu(x))))
-        O4D_TRY(linear_launch(w.x, nq, H, H, d.fc0_w[b], d.fc0_b[b], H, nullptr, 0, w.h, H, O4D_RELU_IN, prec, st));
-        O4D_TRY(linear_launch(w.h, nq, H, H, d.fc1_w[b], d.fc1_b[b], H, w.x, H, w.x, H, O4D_RELU_IN, prec, st));
+        O4D_TRY(linear_ps_launch(&ps, w.x, nq, H, H, d.fc0_w[b], H, d.fc0_b[b], H, nullptr, 0, w.h, H, O4D_RELU_IN, prec, st));
+        O4D_TRY(linear_ps_launch(&ps, w.h, nq, H, H, d.fc1_w[b], H, d.fc1_b[b], H, w.x, H, w.x, H, O4D_RELU_IN, prec, st));
         if (d.use_pt[b] >= 0) {
             // implicit.py:421-439 -> modules.py:61-65 cross attention onto the abstract cloud
             const int j = d.use_pt[b];
             PtBlockParams pp = PtBlockParams::from(d.pt[j]);
-            O4D_TRY(linear_launch(w.x, nq, H, H, pp.w1, pp.b1, H, nullptr, 0, w.y, H, 0, prec, st));
-            O4D_TRY(linear_launch(w.y, nq, H, H, pp.wq, nullptr, H, nullptr, 0, w.h, H, 0, prec, st));
+            pp.ps = &ps;
+            O4D_TRY(linear_ps_launch(&ps, w.x, nq, H, H, pp.w1, H, pp.b1, H, nullptr, 0, w.y, H, 0, prec, st));
+            O4D_TRY(linear_ps_launch(&ps, w.y, nq, H, H, pp.wq, H, nullptr, H, nullptr, 0, w.h, H, 0, prec, st));
             O4D_TRY(attn_core_launch(pp, w.h, s.ktab[j], s.vtab[j], query, c->d_in, s.abs_xyz, 3, w.idx_c, nq, H,
                                      c->cross_attn_neighbors, w.x, w.x, prec, w.sub, w.sub_bytes, st));
         }

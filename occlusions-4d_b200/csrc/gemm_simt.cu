@@ -125,10 +125,21 @@ int linear_ldw_launch(const float* A, int64_t rows, int64_t k, int64_t lda, cons
                 (long long)rows, (long long)k, (long long)n);
     O4D_REQUIRE(lda >= k && ldw >= k && ldc >= n && (!R || ldr >= n), "linear: bad leading dimension");
     O4D_REQUIRE(precision >= 0 && precision <= 2, "linear: precision %d not in {0,1,2}", precision);
+    return linear_ps_launch(nullptr, A, rows, k, lda, W, ldw, bias, n, R, ldr, C, ldc, flags, precision, st);
+}
+
+int linear_ps_launch(const PackedSet* ps, const float* A, int64_t rows, int64_t k, int64_t lda, const float* W,
+                     int64_t ldw, const float* bias, int64_t n, const float* R, int64_t ldr, float* C,
+                     int64_t ldc, int flags, int precision, cudaStream_t st) {
     ProfScope prof(PROF_LINEAR, 2.0 * (double)rows * (double)k * (double)n, st);
-    if (precision != 0 && ldw == k) {
-        int rc = linear_tc_launch(A, rows, k, lda, W, bias, n, R, ldr, C, ldc, flags, precision, st);
-        if (rc != O4D_E_UNSUPPORTED) return rc;
+    if (precision != 0 && tc_shape_ok(rows, k, n)) {
+        const void* packed = ps ? ps->find(W) : nullptr;
+        if (packed)
+            return linear_tc_packed_launch(A, rows, k, lda, packed, n, bias, R, ldr, C, ldc, flags, precision, st);
+        if (ldw == k) {
+            int rc = linear_tc_launch(A, rows, k, lda, W, bias, n, R, ldr, C, ldc, flags, precision, st);
+            if (rc != O4D_E_UNSUPPORTED) return rc;
+        }
     }
     return linear_simt_launch(A, rows, k, lda, W, ldw, bias, n, R, ldr, C, ldc, flags, st);
 }

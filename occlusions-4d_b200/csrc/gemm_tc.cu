@@ -1,12 +1,386 @@
-// tcgen05 dense layer (placeholder until the tensor-core path lands: every shape is
-// declined, so callers fall through to the CUDA-core kernel).
+// tcgen05 dense layer:  C = post(pre(A) @ W^T + bias) [+ R]   with fp32 tensors in HBM.
+//
+// The reference runs every nn.Linear as a cuBLAS fp32 SGEMM.  Here the contraction runs on
+// the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM) while keeping
+// fp32-grade results: both operands are split on the fly into bf16 hi + bf16 lo
+// (x = hi + lo + O(2^-17 |x|)) and three MMAs accumulate hi*hi + lo*hi + hi*lo into the
+// same fp32 TMEM accumulator ("bf16x3", precision 1).  precision 2 issues only hi*hi.
+//
+// Per CTA: one 128 x BN output tile (BN <= 256 TMEM columns), K walked in chunks of 32.
+//   warps 0-3  A producers: coalesced fp32 loads (optionally ReLU), hi/lo split, 16-byte
+//              stores into the K-major no-swizzle core-matrix layout the UMMA descriptor
+//              describes; after the main loop the same warps run the epilogue
+//              (tcgen05.ld 32x32b -> bias / ReLU / residual -> global).
+//   warp 4     allocates TMEM; lane 0 streams the pre-packed weight tiles (hi+lo image of a
+//              BN x 32 slab, already in shared-memory layout) with cp.async.bulk (TMA engine,
+//              mbarrier complete_tx).
+//   warp 5     lane 0 issues tcgen05.mma and commits to the stage's "empty" mbarrier.
+// Two CTAs are resident per SM (2 x ~97 KB smem, 2 x 256 TMEM columns), so one CTA's
+// epilogue overlaps the other's main loop.
 #include "o4d_common.cuh"
+#include <cuda_bf16.h>
 
 namespace o4d {
-int linear_tc_launch(const float*, int64_t, int64_t, int64_t, const float*, const float*, int64_t,
-                     const float*, int64_t, float*, int64_t, int, int, cudaStream_t) {
-    return O4D_E_UNSUPPORTED;
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int BK = 32;
+constexpr int STAGES = 2;
+constexpr int THREADS = 192;
+constexpr int A_HALF_BYTES = BM * BK * 2;          // one bf16 image of the A slab (8 KB)
+constexpr int BN_MAX = 256;
+constexpr int STAGE_BYTES = 2 * A_HALF_BYTES + 2 * BN_MAX * BK * 2;  // 48 KB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t a, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t a) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t a, uint32_t tx) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(tx) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t a, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(a), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) {
+    if (mbar_try_wait(a, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(a, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(mbar)
+                 : "memory");
+}
+
+// K-major, no-swizzle shared-memory matrix descriptor: 8 x 16 B core matrices; LBO = byte
+// distance between the two core matrices of one K=16 step, SBO = distance between 8-row groups.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+    return d;                // layout_type 0 = no swizzle, base_offset 0
+}
+
+// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M = 128.
+__device__ __forceinline__ uint32_t umma_idesc(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t mbar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+    hi = __float2bfloat16_rn(x);
+    lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+struct PackMeta {
+    int n, k;      // logical weight shape
+    int bn;        // tile width (multiple of 16, <= 256)
+    int ntiles;    // ceil(n / bn)
+    int kchunks;   // ceil(k / 32)
+};
+
+__host__ __device__ inline PackMeta pack_meta(int n, int k) {
+    PackMeta m;
+    m.n = n;
+    m.k = k;
+    int tiles = (n + BN_MAX - 1) / BN_MAX;
+    int bn = (n + tiles - 1) / tiles;
+    bn = (bn + 15) / 16 * 16;
+    m.bn = bn;
+    m.ntiles = (n + bn - 1) / bn;
+    m.kchunks = (k + BK - 1) / BK;
+    return m;
+}
+
+__host__ __device__ inline size_t pack_bytes(const PackMeta& m) {
+    return (size_t)m.ntiles * m.kchunks * 2 * m.bn * BK * 2;
+}
+
+// W (n, k) fp32 row-major (ldw) -> per (n-tile, k-chunk): [hi image][lo image], each
+// [kc = 4][row-group = bn/8][8 rows][8 bf16] -- exactly the shared-memory image of the slab.
+__global__ void pack_weight_kernel(const float* __restrict__ W, int64_t ldw, PackMeta m, __nv_bfloat16* __restrict__ out) {
+    const int64_t slab_elems = (int64_t)m.bn * BK;
+    const int64_t total = (int64_t)m.ntiles * m.kchunks * slab_elems;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t slab = e / slab_elems;
+        const int within = (int)(e % slab_elems);
+        const int t = (int)(slab / m.kchunks), c = (int)(slab % m.kchunks);
+        const int kc = within / (m.bn * 8);
+        const int rem = within % (m.bn * 8);
+        const int row = rem / 8, el = rem % 8;      // row = rg*8 + r8
+        const int gn = t * m.bn + row, gk = c * BK + kc * 8 + el;
+        float v = (gn < m.n && gk < m.k) ? W[(int64_t)gn * ldw + gk] : 0.f;
+        __nv_bfloat16 hi, lo;
+        split_bf16(v, hi, lo);
+        out[slab * 2 * slab_elems + within] = hi;
+        out[slab * 2 * slab_elems + slab_elems + within] = lo;
+    }
+}
+
+__global__ void __launch_bounds__(THREADS, 2)
+linear_tc_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda, const __nv_bfloat16* __restrict__ Wp,
+                 PackMeta m, const float* __restrict__ bias, const float* R, int64_t ldr, float* C, int64_t ldc,
+                 int flags, int split) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);  // full[2], empty[2], accum
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row0 = (int64_t)blockIdx.x * BM;
+    const int tile_n = blockIdx.y;
+    const int bn = m.bn;
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]), accum_bar = smem_u32(&bars[2 * STAGES]);
+    const uint32_t smem_base = smem_u32(smem);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full0 + 8 * s, 5);   // 4 producer warps + the weight-copy thread
+            mbar_init(empty0 + 8 * s, 1);  // one tcgen05.commit
+        }
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int nchunks = m.kchunks;
+    const uint32_t b_half_bytes = (uint32_t)bn * BK * 2;
+
+    if (warp < 4) {
+        // ------------------------------------------------------------ A producers
+        const bool relu_in = flags & O4D_RELU_IN;
+        const int kc = lane >> 3, rr = lane & 7;
+        for (int c = 0; c < nchunks; ++c) {
+            const int s = c % STAGES;
+            const uint32_t ph = (uint32_t)(c / STAGES) & 1u;
+            mbar_wait(empty0 + 8 * s, ph ^ 1u);
+            uint8_t* a_hi = smem + s * STAGE_BYTES;
+            uint8_t* a_lo = a_hi + A_HALF_BYTES;
+            const int gk = c * BK + kc * 8;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int rg = warp * 4 + g;                  // 8-row group inside the 128-row tile
+                const int64_t grow = row0 + rg * 8 + rr;
+                float v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = 0.f;
+                if (grow < rows) {
+                    const float* src = A + grow * lda + gk;
+                    if (gk + 8 <= k && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+                        const float4 p0 = *reinterpret_cast<const float4*>(src);
+                        const float4 p1 = *reinterpret_cast<const float4*>(src + 4);
+                        v[0] = p0.x; v[1] = p0.y; v[2] = p0.z; v[3] = p0.w;
+                        v[4] = p1.x; v[5] = p1.y; v[6] = p1.z; v[7] = p1.w;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            if (gk + i < k) v[i] = src[i];
+                    }
+                }
+                __align__(16) __nv_bfloat16 h[8];
+                __align__(16) __nv_bfloat16 l[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float x = relu_in ? fmaxf(v[i], 0.f) : v[i];
+                    split_bf16(x, h[i], l[i]);
+                }
+                const int off = kc * (BM * 16) + rg * 128 + rr * 16;   // [kc][row group][row][16 B]
+                *reinterpret_cast<uint4*>(a_hi + off) = *reinterpret_cast<const uint4*>(h);
+                *reinterpret_cast<uint4*>(a_lo + off) = *reinterpret_cast<const uint4*>(l);
+            }
+            fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full0 + 8 * s);
+        }
+        // ------------------------------------------------------------ epilogue
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+        const bool relu_out = flags & O4D_RELU_OUT;
+        const int64_t grow = row0 + warp * 32 + lane;
+        const int col_base = tile_n * bn;
+        const uint32_t taddr_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+        for (int c0 = 0; c0 < bn; c0 += 16) {
+            float v[16];
+            tmem_ld16(taddr_row + (uint32_t)c0, v);     // warp-collective: every lane executes it
+            if (grow < rows) {
+                const int gc0 = col_base + c0;
+                float* dst = C + grow * ldc + gc0;
+                const float* res = R ? R + grow * ldr + gc0 : nullptr;
+                if (gc0 + 16 <= m.n) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float x = v[i] + (bias ? bias[gc0 + i] : 0.f);
+                        if (relu_out) x = fmaxf(x, 0.f);
+                        if (res) x += res[i];
+                        v[i] = x;
+                    }
+                    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4)
+                            *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) dst[i] = v[i];
+                    }
+                } else {
+                    for (int i = 0; i < 16 && gc0 + i < m.n; ++i) {
+                        float x = v[i] + (bias ? bias[gc0 + i] : 0.f);
+                        if (relu_out) x = fmaxf(x, 0.f);
+                        if (res) x += res[i];
+                        dst[i] = x;
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    } else if (warp == 4) {
+        // ------------------------------------------------------------ weight slabs via the TMA engine
+        if (lane == 0) {
+            const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(Wp) + (size_t)tile_n * nchunks * 2 * b_half_bytes;
+            for (int c = 0; c < nchunks; ++c) {
+                const int s = c % STAGES;
+                const uint32_t ph = (uint32_t)(c / STAGES) & 1u;
+                mbar_wait(empty0 + 8 * s, ph ^ 1u);
+                const uint32_t dst = smem_base + s * STAGE_BYTES + 2 * A_HALF_BYTES;
+                mbar_arrive_expect_tx(full0 + 8 * s, 2 * b_half_bytes);
+                bulk_g2s(dst, wsrc + (size_t)c * 2 * b_half_bytes, 2 * b_half_bytes, full0 + 8 * s);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc(bn);
+            const uint32_t lbo_a = BM * 16, lbo_b = (uint32_t)bn * 16;
+            for (int c = 0; c < nchunks; ++c) {
+                const int s = c % STAGES;
+                const uint32_t ph = (uint32_t)(c / STAGES) & 1u;
+                mbar_wait(full0 + 8 * s, ph);
+                tc_fence_after();
+                const uint32_t a_hi = smem_base + s * STAGE_BYTES;
+                const uint32_t a_lo = a_hi + A_HALF_BYTES;
+                const uint32_t b_hi = a_hi + 2 * A_HALF_BYTES;
+                const uint32_t b_lo = b_hi + b_half_bytes;
+#pragma unroll
+                for (int ks = 0; ks < BK / 16; ++ks) {
+                    const uint64_t da_hi = umma_desc(a_hi + ks * 2 * lbo_a, lbo_a, 128);
+                    const uint64_t db_hi = umma_desc(b_hi + ks * 2 * lbo_b, lbo_b, 128);
+                    umma_f16(tmem_base, da_hi, db_hi, idesc, (c | ks) ? 1u : 0u);
+                    if (split) {
+                        const uint64_t da_lo = umma_desc(a_lo + ks * 2 * lbo_a, lbo_a, 128);
+                        const uint64_t db_lo = umma_desc(b_lo + ks * 2 * lbo_b, lbo_b, 128);
+                        umma_f16(tmem_base, da_lo, db_hi, idesc, 1u);
+                        umma_f16(tmem_base, da_hi, db_lo, idesc, 1u);
+                    }
+                }
+                umma_commit(empty0 + 8 * s);          // frees the stage when these MMAs retire
+            }
+            umma_commit(accum_bar);                   // accumulator complete -> epilogue
+        }
+    }
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    }
+}
+
+}  // namespace tc
+
+size_t tc_pack_bytes(int64_t n, int64_t k) { return tc::pack_bytes(tc::pack_meta((int)n, (int)k)); }
+
+int tc_pack_launch(const float* W, int64_t n, int64_t k, int64_t ldw, void* packed, cudaStream_t st) {
+    tc::PackMeta m = tc::pack_meta((int)n, (int)k);
+    const int64_t total = (int64_t)m.ntiles * m.kchunks * m.bn * tc::BK;
+    int64_t blocks = cdiv(total, 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    tc::pack_weight_kernel<<<(unsigned)blocks, 256, 0, st>>>(W, ldw, m, (__nv_bfloat16*)packed);
+    O4D_LAUNCH_CHECK();
+    return 0;
+}
+
+bool tc_shape_ok(int64_t rows, int64_t k, int64_t n) { return rows >= 1024 && k >= 32 && n >= 32 && k <= 65536 && n <= 65536; }
+
+int linear_tc_packed_launch(const float* A, int64_t rows, int64_t k, int64_t lda, const void* packed, int64_t n,
+                            const float* bias, const float* R, int64_t ldr, float* C, int64_t ldc, int flags,
+                            int precision, cudaStream_t st) {
+    if (rows == 0) return 0;
+    static bool attr_done = false;
+    if (!attr_done) {
+        O4D_CUDA(cudaFuncSetAttribute(tc::linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+        attr_done = true;
+    }
+    tc::PackMeta m = tc::pack_meta((int)n, (int)k);
+    dim3 grid((unsigned)cdiv(rows, tc::BM), (unsigned)m.ntiles);
+    tc::linear_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(A, rows, (int)k, lda, (const __nv_bfloat16*)packed, m, bias, R,
+                                                                    ldr, C, ldc, flags, precision == 1 ? 1 : 0);
+    O4D_LAUNCH_CHECK();
+    return 0;
+}
+
+// Un-packed entry: packs the weight into a stream-ordered temporary first (generic C-ABI
+// calls; the decoder keeps its weights packed in the scene buffer instead).
+int linear_tc_launch(const float* A, int64_t rows, int64_t k, int64_t lda, const float* W, const float* bias,
+                     int64_t n, const float* R, int64_t ldr, float* C, int64_t ldc, int flags, int precision,
+                     cudaStream_t st) {
+    if (!tc_shape_ok(rows, k, n)) return O4D_E_UNSUPPORTED;
+    void* packed = nullptr;
+    O4D_CUDA(cudaMallocAsync(&packed, tc_pack_bytes(n, k), st));
+    int rc = tc_pack_launch(W, n, k, k, packed, st);
+    if (rc == 0) rc = linear_tc_packed_launch(A, rows, k, lda, packed, n, bias, R, ldr, C, ldc, flags, precision, st);
+    cudaFreeAsync(packed, st);
+    return rc;
+}
+
 }  // namespace o4d
 
-extern "C" int o4d_has_tcgen05(void) { return 0; }
+extern "C" int o4d_has_tcgen05(void) { return 1; }

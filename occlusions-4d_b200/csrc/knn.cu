@@ -181,7 +181,7 @@ int knn_launch(const float* query, int64_t nq, int64_t ldq, const float* ref, in
 extern "C" int o4d_knn_f32(const float* query, int64_t nq, int64_t ldq, const float* ref, int64_t m,
                            int64_t ldr, int k, int sqrt_dist, int64_t* idx_out, float* dist_out,
                            void* stream) {
-    O4D_REQUIRE(idx_out || dist_out, "o4d_knn_f32: no output requested");
+    O4D_REQUIRE(nq == 0 || idx_out || dist_out, "o4d_knn_f32: no output requested");
     return o4d::knn_launch(query, nq, ldq, ref, m, ldr, k, sqrt_dist, nullptr, idx_out, dist_out,
                            (cudaStream_t)stream);
 }

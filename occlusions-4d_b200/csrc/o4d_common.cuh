@@ -98,8 +98,36 @@ int linear_tc_launch(const float* A, int64_t rows, int64_t k, int64_t lda, const
                      const float* bias, int64_t n, const float* R, int64_t ldr, float* C,
                      int64_t ldc, int flags, int precision, cudaStream_t st);
 
+// Pre-packed (bf16 hi/lo, shared-memory image) weights for the tcgen05 path, looked up by the
+// fp32 weight pointer they were packed from.
+size_t tc_pack_bytes(int64_t n, int64_t k);
+int tc_pack_launch(const float* W, int64_t n, int64_t k, int64_t ldw, void* packed, cudaStream_t st);
+bool tc_shape_ok(int64_t rows, int64_t k, int64_t n);
+int linear_tc_packed_launch(const float* A, int64_t rows, int64_t k, int64_t lda, const void* packed, int64_t n,
+                            const float* bias, const float* R, int64_t ldr, float* C, int64_t ldc, int flags,
+                            int precision, cudaStream_t st);
+struct PackedSet {
+    static constexpr int CAP = 96;
+    const float* key[CAP];
+    const void* packed[CAP];
+    int count = 0;
+    void add(const float* w, const void* p) {
+        if (count < CAP) { key[count] = w; packed[count] = p; ++count; }
+    }
+    const void* find(const float* w) const {
+        for (int i = 0; i < count; ++i)
+            if (key[i] == w) return packed[i];
+        return nullptr;
+    }
+};
+// linear_ldw_launch that prefers a pre-packed weight from `ps` (may be null).
+int linear_ps_launch(const PackedSet* ps, const float* A, int64_t rows, int64_t k, int64_t lda, const float* W,
+                     int64_t ldw, const float* bias, int64_t n, const float* R, int64_t ldr, float* C,
+                     int64_t ldc, int flags, int precision, cudaStream_t st);
+
 struct PtBlockParams {
     const float *w1, *b1, *wq, *wk, *wv, *wp1, *bp1, *wp2, *bp2, *wa1, *ba1, *wa2, *ba2, *w3, *b3;
+    const PackedSet* ps = nullptr;  // optional pre-packed tcgen05 weights
     static PtBlockParams from(const float* const* p) {
         PtBlockParams r;
         r.w1 = p[0]; r.b1 = p[1]; r.wq = p[2]; r.wk = p[3]; r.wv = p[4];

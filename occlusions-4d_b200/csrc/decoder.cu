@@ -53,6 +53,9 @@ struct SceneView {
     float* zg;        // (n_blocks, H)   W_z[:, :Dg] g + b_z
     float* ktab[O4D_MAX_BLOCKS];  // (m, H) per cross layer
     float* vtab[O4D_MAX_BLOCKS];
+    char* tables[O4D_MAX_BLOCKS];  // attention tables (Ka, Wc, cvec) per cross layer
+    size_t tables_bytes;
+    char* fused[O4D_MAX_BLOCKS];   // packed weights of the fused attention kernel (or null)
     size_t pack_off;  // byte offset of the pre-packed tcgen05 weights (precision != 0)
     size_t bytes;
 };
@@ -69,6 +72,13 @@ static SceneView scene_view(const o4d_decoder_config* c, int64_t m, void* base) 
         s.ktab[j] = a.get<float>((size_t)m * c->d_hidden);
         s.vtab[j] = a.get<float>((size_t)m * c->d_hidden);
     }
+    s.tables_bytes = attn_tables_bytes(m, c->d_hidden);
+    for (int j = 0; j < c->cross_attn_layers; ++j) s.tables[j] = a.get<char>(s.tables_bytes);
+    const bool use_fused = c->precision != 0 && attn_fused_supported(c->d_hidden, c->cross_attn_neighbors);
+    for (int j = 0; j < c->cross_attn_layers; ++j)
+        s.fused[j] = use_fused ? a.get<char>(attn_fused_pack_bytes(c->d_hidden)) : nullptr;
+    if (use_fused && base == nullptr)
+        for (int j = 0; j < c->cross_attn_layers; ++j) s.fused[j] = nullptr;
     s.pack_off = a.off;
     a.get<char>(packed_total_bytes(c));
     s.bytes = a.off;
@@ -77,8 +87,13 @@ static SceneView scene_view(const o4d_decoder_config* c, int64_t m, void* base) 
 
 // Weights the tcgen05 path consumes, in a fixed order: sizing, packing (prepare) and lookup
 // (forward) all walk this list.  fn(weight, n, k, ldw).
+static const float* tables_wc(const SceneView* s, int j, int64_t m, int d) {
+    // second entry of the attn_tables_launch arena: Ka (m, 2d) first, then Wc
+    return s && s->tables[j] ? (const float*)(s->tables[j] + align_up((size_t)m * 2 * d * sizeof(float), 256)) : nullptr;
+}
+
 template <typename F>
-static void for_each_tc_weight(const o4d_decoder_config* c, const DecParams& d, F fn) {
+static void for_each_tc_weight(const o4d_decoder_config* c, const DecParams& d, const SceneView* s, int64_t m, F fn) {
     const int H = c->d_hidden, E = c->d_latent_local, Dg = c->d_latent - c->d_latent_local;
     const int pe_w = c->pos_encoding_freqs > 0 ? c->d_in * (2 * c->pos_encoding_freqs + 1) : c->d_in;
     fn(d.lin_in_w, H, pe_w, pe_w);
@@ -91,9 +106,11 @@ static void for_each_tc_weight(const o4d_decoder_config* c, const DecParams& d, 
         const float* const* p = d.pt[j];
         fn(p ? p[0] : nullptr, H, H, H);           // layer1
         fn(p ? p[2] : nullptr, H, H, H);           // to_q
-        fn(p ? p[9] : nullptr, 2 * H, H, H);       // attn_mlp.0
+        fn(p ? p[9] : nullptr, 2 * H, H, H);       // attn_mlp.0 (per-query part Qa)
         fn(p ? p[11] : nullptr, H, 2 * H, 2 * H);  // attn_mlp.2
         fn(p ? p[13] : nullptr, H, H, H);          // layer3
+        fn(p ? p[7] : nullptr, H, 32, 32);         // pos_mlp.2 (delta)
+        fn(tables_wc(s, j, m, H), 2 * H, 32, 32);  // Wc = attn_mlp.0 . pos_mlp.2
     }
 }
 
@@ -101,14 +118,15 @@ static size_t packed_total_bytes(const o4d_decoder_config* c) {
     if (c->precision == 0) return 0;
     DecParams d = {};
     size_t total = 0;
-    for_each_tc_weight(c, d, [&](const float*, int n, int k, int) { total += align_up(tc_pack_bytes(n, k), 256); });
+    for_each_tc_weight(c, d, nullptr, 0, [&](const float*, int n, int k, int) { total += align_up(tc_pack_bytes(n, k), 256); });
     return total;
 }
 
-static void packed_set(const o4d_decoder_config* c, const DecParams& d, const void* scene, size_t pack_off, PackedSet* ps) {
+static void packed_set(const o4d_decoder_config* c, const DecParams& d, const SceneView& s, int64_t m, const void* scene,
+                       PackedSet* ps) {
     if (c->precision == 0) return;
-    const char* p = (const char*)scene + pack_off;
-    for_each_tc_weight(c, d, [&](const float* w, int n, int k, int) {
+    const char* p = (const char*)scene + s.pack_off;
+    for_each_tc_weight(c, d, &s, m, [&](const float* w, int n, int k, int) {
         ps->add(w, p);
         p += align_up(tc_pack_bytes(n, k), 256);
     });
@@ -139,12 +157,15 @@ int decoder_prepare(const o4d_decoder_config* c, const float* const* P, const fl
         PtBlockParams pp = PtBlockParams::from(d.pt[j]);
         O4D_TRY(linear_launch(s.abs_feat, m, E, E, pp.wk, nullptr, H, nullptr, 0, s.ktab[j], H, 0, 0, st));
         O4D_TRY(linear_launch(s.abs_feat, m, E, E, pp.wv, nullptr, H, nullptr, 0, s.vtab[j], H, 0, 0, st));
+        AttnTables T;
+        O4D_TRY(attn_tables_launch(pp, s.ktab[j], s.vtab[j], m, H, s.tables[j], s.tables_bytes, &T, st));
+        if (s.fused[j]) O4D_TRY(attn_fused_pack_launch(T.wc, pp.wa2, pp.wp2, H, s.fused[j], st));
     }
     if (c->precision != 0) {
         // bf16 hi/lo shared-memory images of every weight the tcgen05 path reads
         char* p = (char*)scene + s.pack_off;
         int rc = 0;
-        for_each_tc_weight(c, d, [&](const float* w, int n, int k, int ldw) {
+        for_each_tc_weight(c, d, &s, m, [&](const float* w, int n, int k, int ldw) {
             if (rc == 0) rc = tc_pack_launch(w, n, k, ldw, p, st);
             p += align_up(tc_pack_bytes(n, k), 256);
         });
@@ -200,7 +221,7 @@ int decoder_forward(const o4d_decoder_config* c, const float* const* P, const vo
     DecParams d;
     dec_unpack(c, P, &d);
     PackedSet ps;
-    packed_set(c, d, scene, s.pack_off, &ps);
+    packed_set(c, d, s, m, scene, &ps);
 
     // implicit.py:328-339  K_l nearest abstract points, inverse-distance blend of their features
     O4D_TRY(knn_launch(query, nq, c->d_in, s.abs_xyz, m, 3, c->num_local_features, 1, w.idx_l, nullptr, w.dist_l, st));
@@ -229,7 +250,16 @@ int decoder_forward(const o4d_decoder_config* c, const float* const* P, const vo
             pp.ps = &ps;
             O4D_TRY(linear_ps_launch(&ps, w.x, nq, H, H, pp.w1, H, pp.b1, H, nullptr, 0, w.y, H, 0, prec, st));
             O4D_TRY(linear_ps_launch(&ps, w.y, nq, H, H, pp.wq, H, nullptr, H, nullptr, 0, w.h, H, 0, prec, st));
-            O4D_TRY(attn_core_launch(pp, w.h, s.ktab[j], s.vtab[j], query, c->d_in, s.abs_xyz, 3, w.idx_c, nq, H,
+            AttnTables T;
+            {
+                Arena ta(s.tables[j], s.tables_bytes);   // same carve-up as attn_tables_launch
+                T.ka = ta.get<float>((size_t)m * 2 * H);
+                T.wc = ta.get<float>((size_t)2 * H * 32);
+                T.cvec = ta.get<float>((size_t)2 * H);
+                T.vtab = s.vtab[j];
+                T.fused = s.fused[j];
+            }
+            O4D_TRY(attn_core_launch(pp, w.h, T, query, c->d_in, s.abs_xyz, 3, w.idx_c, nq, H,
                                      c->cross_attn_neighbors, w.x, w.x, prec, w.sub, w.sub_bytes, st));
         }
     }

@@ -15,7 +15,7 @@ template <int TM, int TN>
 __global__ void __launch_bounds__(256)
 linear_simt_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda,
                    const float* __restrict__ W, int64_t ldw, const float* __restrict__ bias, int n,
-                   const float* R, int64_t ldr, float* C, int64_t ldc, int flags) {
+                   const float* R, int64_t ldr, float* C, int64_t ldc, int flags, RowGather g) {
     constexpr int BM = 16 * TM, BN = 16 * TN;
     __shared__ __align__(16) float As[GS_BK][BM + 4];
     __shared__ __align__(16) float Ws[GS_BK][BN + 4];
@@ -71,12 +71,20 @@ linear_simt_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda
     for (int i = 0; i < TM; ++i) {
         int64_t gr = row0 + ty + 16 * i;
         if (gr >= rows) continue;
+        const float* gq = nullptr;
+        const float* gk = nullptr;
+        if (g.qa) {
+            const int64_t ar = g.row_offset + gr;
+            gq = g.qa + (ar / g.knbr) * n;
+            gk = g.ka + (int64_t)g.nbr[ar] * n;
+        }
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
             int gc = col0 + tx + 16 * j;
             if (gc >= n) continue;
             float v = acc[i][j];
             if (bias) v += bias[gc];
+            if (gq) v += gq[gc] - gk[gc];
             if (relu_out) v = fmaxf(v, 0.f);
             if (R) v += R[gr * ldr + gc];
             C[gr * ldc + gc] = v;
@@ -86,20 +94,22 @@ linear_simt_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda
 
 int linear_simt_launch(const float* A, int64_t rows, int64_t k, int64_t lda, const float* W,
                        int64_t ldw, const float* bias, int64_t n, const float* R, int64_t ldr,
-                       float* C, int64_t ldc, int flags, cudaStream_t st) {
+                       float* C, int64_t ldc, int flags, cudaStream_t st, const RowGather* gp = nullptr) {
     if (rows == 0) return 0;
+    RowGather g;
+    if (gp) g = *gp;
     if (n > 96 && rows >= 8192) {
         dim3 grid((unsigned)cdiv(rows, 128), (unsigned)cdiv(n, 128));
-        linear_simt_kernel<8, 8><<<grid, 256, 0, st>>>(A, rows, (int)k, lda, W, ldw, bias, (int)n, R, ldr, C, ldc, flags);
+        linear_simt_kernel<8, 8><<<grid, 256, 0, st>>>(A, rows, (int)k, lda, W, ldw, bias, (int)n, R, ldr, C, ldc, flags, g);
     } else if (n > 48) {
         dim3 grid((unsigned)cdiv(rows, 128), (unsigned)cdiv(n, 64));
-        linear_simt_kernel<8, 4><<<grid, 256, 0, st>>>(A, rows, (int)k, lda, W, ldw, bias, (int)n, R, ldr, C, ldc, flags);
+        linear_simt_kernel<8, 4><<<grid, 256, 0, st>>>(A, rows, (int)k, lda, W, ldw, bias, (int)n, R, ldr, C, ldc, flags, g);
     } else if (rows >= 4096) {
         dim3 grid((unsigned)cdiv(rows, 128), (unsigned)cdiv(n, 16));
-        linear_simt_kernel<8, 1><<<grid, 256, 0, st>>>(A, rows, (int)k, lda, W, ldw, bias, (int)n, R, ldr, C, ldc, flags);
+        linear_simt_kernel<8, 1><<<grid, 256, 0, st>>>(A, rows, (int)k, lda, W, ldw, bias, (int)n, R, ldr, C, ldc, flags, g);
     } else {
         dim3 grid((unsigned)cdiv(rows, 16), (unsigned)cdiv(n, 16));
-        linear_simt_kernel<1, 1><<<grid, 256, 0, st>>>(A, rows, (int)k, lda, W, ldw, bias, (int)n, R, ldr, C, ldc, flags);
+        linear_simt_kernel<1, 1><<<grid, 256, 0, st>>>(A, rows, (int)k, lda, W, ldw, bias, (int)n, R, ldr, C, ldc, flags, g);
     }
     O4D_LAUNCH_CHECK();
     return 0;
@@ -130,18 +140,18 @@ int linear_ldw_launch(const float* A, int64_t rows, int64_t k, int64_t lda, cons
 
 int linear_ps_launch(const PackedSet* ps, const float* A, int64_t rows, int64_t k, int64_t lda, const float* W,
                      int64_t ldw, const float* bias, int64_t n, const float* R, int64_t ldr, float* C,
-                     int64_t ldc, int flags, int precision, cudaStream_t st) {
+                     int64_t ldc, int flags, int precision, cudaStream_t st, const RowGather* g) {
     ProfScope prof(PROF_LINEAR, 2.0 * (double)rows * (double)k * (double)n, st);
     if (precision != 0 && tc_shape_ok(rows, k, n)) {
         const void* packed = ps ? ps->find(W) : nullptr;
         if (packed)
-            return linear_tc_packed_launch(A, rows, k, lda, packed, n, bias, R, ldr, C, ldc, flags, precision, st);
+            return linear_tc_packed_launch(A, rows, k, lda, packed, n, bias, R, ldr, C, ldc, flags, precision, st, g);
         if (ldw == k) {
-            int rc = linear_tc_launch(A, rows, k, lda, W, bias, n, R, ldr, C, ldc, flags, precision, st);
+            int rc = linear_tc_launch(A, rows, k, lda, W, bias, n, R, ldr, C, ldc, flags, precision, st, g);
             if (rc != O4D_E_UNSUPPORTED) return rc;
         }
     }
-    return linear_simt_launch(A, rows, k, lda, W, ldw, bias, n, R, ldr, C, ldc, flags, st);
+    return linear_simt_launch(A, rows, k, lda, W, ldw, bias, n, R, ldr, C, ldc, flags, st, g);
 }
 
 }  // namespace o4d

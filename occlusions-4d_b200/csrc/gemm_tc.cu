@@ -165,7 +165,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ W, int64_t ldw, Pac
 __global__ void __launch_bounds__(THREADS, 2)
 linear_tc_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda, const __nv_bfloat16* __restrict__ Wp,
                  PackMeta m, const float* __restrict__ bias, const float* R, int64_t ldr, float* C, int64_t ldc,
-                 int flags, int split) {
+                 int flags, int split, RowGather g) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);  // full[2], empty[2], accum
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
@@ -249,6 +249,13 @@ linear_tc_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda, 
         const int64_t grow = row0 + warp * 32 + lane;
         const int col_base = tile_n * bn;
         const uint32_t taddr_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const float* gq = nullptr;   // row-dependent additive term (attention MLP first layer)
+        const float* gk = nullptr;
+        if (g.qa && grow < rows) {
+            const int64_t ar = g.row_offset + grow;
+            gq = g.qa + (ar / g.knbr) * m.n;
+            gk = g.ka + (int64_t)g.nbr[ar] * m.n;
+        }
         for (int c0 = 0; c0 < bn; c0 += 16) {
             float v[16];
             tmem_ld16(taddr_row + (uint32_t)c0, v);     // warp-collective: every lane executes it
@@ -260,6 +267,7 @@ linear_tc_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda, 
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         float x = v[i] + (bias ? bias[gc0 + i] : 0.f);
+                        if (gq) x += gq[gc0 + i] - gk[gc0 + i];
                         if (relu_out) x = fmaxf(x, 0.f);
                         if (res) x += res[i];
                         v[i] = x;
@@ -275,6 +283,7 @@ linear_tc_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda, 
                 } else {
                     for (int i = 0; i < 16 && gc0 + i < m.n; ++i) {
                         float x = v[i] + (bias ? bias[gc0 + i] : 0.f);
+                        if (gq) x += gq[gc0 + i] - gk[gc0 + i];
                         if (relu_out) x = fmaxf(x, 0.f);
                         if (res) x += res[i];
                         dst[i] = x;
@@ -352,8 +361,10 @@ bool tc_shape_ok(int64_t rows, int64_t k, int64_t n) { return rows >= 1024 && k 
 
 int linear_tc_packed_launch(const float* A, int64_t rows, int64_t k, int64_t lda, const void* packed, int64_t n,
                             const float* bias, const float* R, int64_t ldr, float* C, int64_t ldc, int flags,
-                            int precision, cudaStream_t st) {
+                            int precision, cudaStream_t st, const RowGather* gp) {
     if (rows == 0) return 0;
+    RowGather g;
+    if (gp) g = *gp;
     static bool attr_done = false;
     if (!attr_done) {
         O4D_CUDA(cudaFuncSetAttribute(tc::linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
@@ -362,7 +373,7 @@ int linear_tc_packed_launch(const float* A, int64_t rows, int64_t k, int64_t lda
     tc::PackMeta m = tc::pack_meta((int)n, (int)k);
     dim3 grid((unsigned)cdiv(rows, tc::BM), (unsigned)m.ntiles);
     tc::linear_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(A, rows, (int)k, lda, (const __nv_bfloat16*)packed, m, bias, R,
-                                                                    ldr, C, ldc, flags, precision == 1 ? 1 : 0);
+                                                                    ldr, C, ldc, flags, precision == 1 ? 1 : 0, g);
     O4D_LAUNCH_CHECK();
     return 0;
 }
@@ -371,12 +382,12 @@ int linear_tc_packed_launch(const float* A, int64_t rows, int64_t k, int64_t lda
 // calls; the decoder keeps its weights packed in the scene buffer instead).
 int linear_tc_launch(const float* A, int64_t rows, int64_t k, int64_t lda, const float* W, const float* bias,
                      int64_t n, const float* R, int64_t ldr, float* C, int64_t ldc, int flags, int precision,
-                     cudaStream_t st) {
+                     cudaStream_t st, const RowGather* g) {
     if (!tc_shape_ok(rows, k, n)) return O4D_E_UNSUPPORTED;
     void* packed = nullptr;
     O4D_CUDA(cudaMallocAsync(&packed, tc_pack_bytes(n, k), st));
     int rc = tc_pack_launch(W, n, k, k, packed, st);
-    if (rc == 0) rc = linear_tc_packed_launch(A, rows, k, lda, packed, n, bias, R, ldr, C, ldc, flags, precision, st);
+    if (rc == 0) rc = linear_tc_packed_launch(A, rows, k, lda, packed, n, bias, R, ldr, C, ldc, flags, precision, st, g);
     cudaFreeAsync(packed, st);
     return rc;
 }

@@ -80,6 +80,17 @@ struct Arena {
     }
 };
 
+// Optional row-dependent epilogue term of a dense layer: before the output ReLU,
+//   C[r, c] += qa[(row_offset + r) / knbr, c] - ka[nbr[row_offset + r], c]
+// (rows are (query, neighbour) pairs; qa / ka have the layer's n columns).
+struct RowGather {
+    const float* qa = nullptr;
+    const float* ka = nullptr;
+    const int32_t* nbr = nullptr;
+    int knbr = 1;
+    int64_t row_offset = 0;
+};
+
 // ---- internal launchers shared between translation units (all async on `st`) ----
 int knn_launch(const float* query, int64_t nq, int64_t ldq, const float* ref, int64_t m,
                int64_t ldr, int k, int sqrt_dist, int32_t* idx32, int64_t* idx64, float* dist,
@@ -96,7 +107,7 @@ int linear_ldw_launch(const float* A, int64_t rows, int64_t k, int64_t lda, cons
 // tcgen05 path (gemm_tc.cu); returns O4D_E_UNSUPPORTED when the shape cannot use it.
 int linear_tc_launch(const float* A, int64_t rows, int64_t k, int64_t lda, const float* W,
                      const float* bias, int64_t n, const float* R, int64_t ldr, float* C,
-                     int64_t ldc, int flags, int precision, cudaStream_t st);
+                     int64_t ldc, int flags, int precision, cudaStream_t st, const RowGather* g = nullptr);
 
 // Pre-packed (bf16 hi/lo, shared-memory image) weights for the tcgen05 path, looked up by the
 // fp32 weight pointer they were packed from.
@@ -105,7 +116,7 @@ int tc_pack_launch(const float* W, int64_t n, int64_t k, int64_t ldw, void* pack
 bool tc_shape_ok(int64_t rows, int64_t k, int64_t n);
 int linear_tc_packed_launch(const float* A, int64_t rows, int64_t k, int64_t lda, const void* packed, int64_t n,
                             const float* bias, const float* R, int64_t ldr, float* C, int64_t ldc, int flags,
-                            int precision, cudaStream_t st);
+                            int precision, cudaStream_t st, const RowGather* g = nullptr);
 struct PackedSet {
     static constexpr int CAP = 96;
     const float* key[CAP];
@@ -123,7 +134,7 @@ struct PackedSet {
 // linear_ldw_launch that prefers a pre-packed weight from `ps` (may be null).
 int linear_ps_launch(const PackedSet* ps, const float* A, int64_t rows, int64_t k, int64_t lda, const float* W,
                      int64_t ldw, const float* bias, int64_t n, const float* R, int64_t ldr, float* C,
-                     int64_t ldc, int flags, int precision, cudaStream_t st);
+                     int64_t ldc, int flags, int precision, cudaStream_t st, const RowGather* g = nullptr);
 
 struct PtBlockParams {
     const float *w1, *b1, *wq, *wk, *wv, *wp1, *bp1, *wp2, *bp2, *wa1, *ba1, *wa2, *ba2, *w3, *b3;
@@ -140,11 +151,27 @@ struct PtBlockParams {
 // Attention core shared by the encoder (self) and decoder (cross):
 //   out = x_res + W3 . attn(q, ktab, vtab, pos, pos2, nbr) + b3      (n rows, d channels)
 // q (n,d) already projected; ktab/vtab (m,d); nbr (n,k) int32.
+// Per key cloud: V table (m,d), Ka = K W_a1^T (m,2d), Wc = W_a1 W_p2 (2d,32), cvec = W_a1 b_p2 + b_a1.
+struct AttnTables {
+    const float* vtab;
+    const float* ka;
+    const float* wc;
+    const float* cvec;
+    const void* fused = nullptr;   // packed weight images of the fused tcgen05 kernel (attn_fused.cu) or null
+};
+bool attn_fused_supported(int d, int k);
+size_t attn_fused_pack_bytes(int d);
+int attn_fused_pack_launch(const float* wc, const float* wa2, const float* wp2, int d, void* packed, cudaStream_t st);
+int attn_fused_launch(const PtBlockParams& P, const AttnTables& T, const float* qa, const float* pos, int64_t ldpos,
+                      const float* pos2, int64_t ldpos2, const int32_t* nbr, int64_t n, int d, int k, float* out,
+                      int precision, cudaStream_t st);
+size_t attn_tables_bytes(int64_t m, int d);
+int attn_tables_launch(const PtBlockParams& P, const float* ktab, const float* vtab, int64_t m, int d, void* buf,
+                       size_t buf_bytes, AttnTables* out, cudaStream_t st);
 size_t attn_core_workspace_bytes(int64_t n, int d, int k);
-int attn_core_launch(const PtBlockParams& P, const float* q, const float* ktab, const float* vtab,
-                     const float* pos, int64_t ldpos, const float* pos2, int64_t ldpos2,
-                     const int32_t* nbr, int64_t n, int d, int k, const float* x_res, float* out,
-                     int precision, void* ws, size_t ws_bytes, cudaStream_t st);
+int attn_core_launch(const PtBlockParams& P, const float* q, const AttnTables& T, const float* pos, int64_t ldpos,
+                     const float* pos2, int64_t ldpos2, const int32_t* nbr, int64_t n, int d, int k,
+                     const float* x_res, float* out, int precision, void* ws, size_t ws_bytes, cudaStream_t st);
 
 size_t pt_block_ws(int64_t n, int64_t m, int d, int k, bool self_mode);
 int pt_block_launch(const float* const* p, const float* x, int64_t n, int d, const float* pos,

@@ -226,3 +226,40 @@ def test_released_checkpoint_parity(which):
                            [ck['implicit_args']['num_local_features'], ck['implicit_args']['cross_attn_neighbors']])
     assert relerr(out.cpu()[ok], ck['out'][ok]) < TOL
     assert relerr(pen.cpu()[ok][:, :16], ck['penult'][ok]) < TOL
+
+
+# ------------------------------------------------------------ fused attention kernel coverage
+
+@pytest.mark.parametrize('d_hidden,d_local,k_cross,n_query,m_abs', [
+    (416, 288, 14, 1, 300),       # single query: one 9-query tile, 8 of them padding
+    (416, 288, 14, 1003, 531),    # ragged tail tile
+    (416, 288, 16, 777, 100),     # 8 queries x 16 neighbours fill the 128-row tile exactly
+    (416, 288, 12, 500, 2124),    # 10 queries per tile, CARLA-sized abstract cloud
+    (288, 224, 14, 640, 200),     # narrower decoder: two 144-column MMA tiles, 18 hidden chunks
+    (320, 256, 9, 333, 64),       # 14 queries per tile
+])
+def test_fused_attention_decoder_shapes_match_oracle(d_hidden, d_local, k_cross, n_query, m_abs):
+    args = dict(configs.C2_GREATER['implicit_args'], d_hidden=d_hidden, d_latent=d_hidden, d_latent_local=d_local,
+                cross_attn_neighbors=k_cross, n_blocks=2, cross_attn_layers=1, cr_attn_type='c', d_out=7)
+    torch.manual_seed(d_hidden + k_cross)
+    dec = o4d.LocalPclResnetFC(**args).eval()
+    sd = orc.cast_state(dec.state_dict(), torch.float32)
+    g = torch.Generator().manual_seed(n_query)
+    abstract = torch.cat([torch.rand(m_abs, 3, generator=g) * 10 - 5, torch.randn(m_abs, d_local, generator=g)], dim=1)
+    glob = torch.randn(d_hidden - d_local, generator=g)
+    query = torch.cat([torch.rand(n_query, 3, generator=g) * 10 - 5, torch.full((n_query, 1), 3.0)], dim=1)
+    want, want_pen = orc.decoder_forward(sd, args, query, abstract, glob)
+    dec = dec.to(DEV)
+    outs = {}
+    for prec in (0, 1):
+        dec.o4d_precision = prec
+        with torch.no_grad():
+            out, pen = dec(query.to(DEV), abstract.to(DEV), glob.to(DEV), None)
+        outs[prec] = out.cpu()
+        assert relerr(out.cpu(), want) < TOL_TIGHT, (prec, relerr(out.cpu(), want))
+        assert relerr(pen.cpu(), want_pen) < TOL_TIGHT, prec
+    # single-pass bf16 (precision 2) is the fast, lossy mode: documented ~1e-2, must stay sane
+    dec.o4d_precision = 2
+    with torch.no_grad():
+        out2, _ = dec(query.to(DEV), abstract.to(DEV), glob.to(DEV), None)
+    assert relerr(out2.cpu(), want) < 5e-2

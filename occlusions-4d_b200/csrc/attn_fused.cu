@@ -30,17 +30,22 @@ namespace fa {
 
 constexpr int BM = 128;
 constexpr int HC = 32;          // hidden units per chunk == K of the second contraction per chunk
-constexpr int THREADS = 192;
+constexpr int ROW_WARPS = 8;    // two warps per TMEM lane quarter
+constexpr int THREADS = (ROW_WARPS + 2) * 32;
 constexpr int R_BYTES = BM * 32 * 2;         // one bf16 image of a (128 x 32) A operand
+constexpr int NBUF = 3;                      // acc1 (TMEM) / hidden A2 (smem) buffers: MMA1 runs two chunks ahead
+constexpr int WC_STAGES = 4;                 // ring of Wc chunks (4 KB each)
 constexpr int OFF_R = 0;                     // r hi, r lo
-constexpr int OFF_A2 = 2 * R_BYTES;          // 2 buffers x (hi, lo)
-constexpr int OFF_W = OFF_A2 + 4 * R_BYTES;  // weight stages
-constexpr int ACC1_COL = 448;
+constexpr int OFF_A2 = 2 * R_BYTES;          // NBUF x (hi, lo)
 constexpr int WC_BYTES = HC * 32 * 2;        // one bf16 image of a Wc chunk (32 x 32)
-constexpr int STG_LD = 33;                   // padded row stride of the epilogue staging tiles
+constexpr int OFF_WC = OFF_A2 + NBUF * 2 * R_BYTES;
+constexpr int OFF_W = OFF_WC + WC_STAGES * 2 * WC_BYTES;   // two stages of W_a2 chunks
+constexpr int ACC1_COL = 416;                // TMEM: [0, d) logits, [416, 512) three acc1 buffers
+constexpr int STG_LD = 33;                   // padded row pitch (floats) of the epilogue staging tiles
 
-__host__ __device__ inline int wstage_bytes(int d) { return 2 * WC_BYTES + 2 * d * 32 * 2; }
-__host__ __device__ inline int smem_bytes(int d) { return OFF_W + 2 * wstage_bytes(d) + 256; }
+__host__ __device__ inline int w2_bytes(int d) { return 2 * d * 32 * 2; }             // W_a2 chunk, hi + lo
+__host__ __device__ inline int wstage_bytes(int d) { return 2 * WC_BYTES + w2_bytes(d); }  // packed chunk in HBM
+__host__ __device__ inline int smem_bytes(int d) { return OFF_W + 2 * w2_bytes(d) + 256; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t a, uint32_t count) {
@@ -107,6 +112,17 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
 }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// 2^x for x <= 0 (softmax weights): single MUFU, flush-to-zero below 2^-126
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
@@ -128,6 +144,23 @@ __device__ __forceinline__ void store_a_row(uint8_t* hi_img, uint8_t* lo_img, in
     }
 }
 
+// 16 fp32 values (columns [16*half, 16*half+16) of a 32-wide K slab) of one row.
+__device__ __forceinline__ void store_a_half_row(uint8_t* hi_img, uint8_t* lo_img, int row, int half, const float* v) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int kc = half * 2 + q;
+        __align__(16) __nv_bfloat16 h[8];
+        __align__(16) __nv_bfloat16 l[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) split_bf16(v[q * 8 + e], h[e], l[e]);
+        const int off = kc * (BM * 16) + (row >> 3) * 128 + (row & 7) * 16;
+        *reinterpret_cast<uint4*>(hi_img + off) = *reinterpret_cast<const uint4*>(h);
+        *reinterpret_cast<uint4*>(lo_img + off) = *reinterpret_cast<const uint4*>(l);
+    }
+}
+
+__device__ long long g_dbg[16];   // cycle stamps of one tile (diagnostics, read by o4d_debug_read)
+
 struct Params {
     const float* pos; int64_t ldpos;       // query coordinates (n, ldpos)
     const float* pos2; int64_t ldpos2;     // key coordinates (m, ldpos2)
@@ -142,37 +175,42 @@ struct Params {
     float* out;                            // (n, d)
     int64_t n;
     int d, k, tq, split;
-    float inv_sqrt_d;
+    float scale_log2;                      // log2(e) / sqrt(d): softmax evaluated with exp2
 };
 
+template <int KT>   // KT = neighbours per query when known at compile time (0: use p.k)
 __global__ void __launch_bounds__(THREADS, 1) attn_fused_kernel(const Params p) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const int d = p.d, k = p.k;
-    const int wstage = wstage_bytes(d);
+    const int d = p.d;
+    const int k = KT ? KT : p.k;
+    const int w2 = w2_bytes(d);
+    const int wpacked = wstage_bytes(d);
     const int NC = 2 * d / HC;              // hidden chunks
     const int ND = d / 32;                  // output-column chunks of the softmax epilogue
     const int ntile = d > 256 ? 2 : 1;      // MMA2 is issued per n-tile of dn <= 256 columns
     const int dn = d / ntile;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_W + 2 * wstage);
-    // barrier indices
-    enum { W_FULL = 0, W_EMPTY = 2, ACC1_FULL = 4, A2_FULL = 6, A2_EMPTY = 8, R_READY = 10, ACC2_FULL = 11, NBARS = 12 };
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_W + 2 * w2);
+    enum { W_FULL = 0, W_EMPTY = 2, WC_FULL = 4, WC_EMPTY = 8, ACC1_FULL = 12, A2_FULL = 15, A2_EMPTY = 18,
+           R_READY = 21, ACC2_FULL = 22, NBARS = 23 };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
     const uint32_t bar0 = smem_u32(bars);
 #define BAR(i) (bar0 + 8u * (uint32_t)(i))
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = smem_u32(smem);
 
     if (threadIdx.x == 0) {
-        mbar_init(BAR(W_FULL + 0), 1); mbar_init(BAR(W_FULL + 1), 1);
-        mbar_init(BAR(W_EMPTY + 0), 1); mbar_init(BAR(W_EMPTY + 1), 1);
-        mbar_init(BAR(ACC1_FULL + 0), 1); mbar_init(BAR(ACC1_FULL + 1), 1);
-        mbar_init(BAR(A2_FULL + 0), 4); mbar_init(BAR(A2_FULL + 1), 4);
-        mbar_init(BAR(A2_EMPTY + 0), 1); mbar_init(BAR(A2_EMPTY + 1), 1);
-        mbar_init(BAR(R_READY), 4);
+        for (int i = 0; i < 2; ++i) { mbar_init(BAR(W_FULL + i), 1); mbar_init(BAR(W_EMPTY + i), 1); }
+        for (int i = 0; i < WC_STAGES; ++i) { mbar_init(BAR(WC_FULL + i), 1); mbar_init(BAR(WC_EMPTY + i), 1); }
+        for (int i = 0; i < NBUF; ++i) {
+            mbar_init(BAR(ACC1_FULL + i), 1);
+            mbar_init(BAR(A2_FULL + i), ROW_WARPS);
+            mbar_init(BAR(A2_EMPTY + i), 1);
+        }
+        mbar_init(BAR(R_READY), ROW_WARPS);
         mbar_init(BAR(ACC2_FULL), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
+    if (warp == ROW_WARPS) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -182,130 +220,202 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fused_kernel(const Params p) 
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 4) {
+    if (warp < ROW_WARPS) {
         // ================================================================== row warps
-        const int r = threadIdx.x;                       // tile row == TMEM lane
+        // Two warps per TMEM lane quarter: thread (r, half) owns tile row r and columns
+        // [16*half, 16*half+16) of every 32-column chunk.
+        const int r = threadIdx.x & (BM - 1);            // tile row == TMEM lane
+        const int half = threadIdx.x >> 7;
         const int qi = r / k, jn = r - qi * k;
-        const int64_t i = (int64_t)blockIdx.x * p.tq + qi;
+        const int64_t q0 = (int64_t)blockIdx.x * p.tq;
+        const int64_t i = q0 + qi;
         const bool valid = (qi < p.tq) && (i < p.n);
         const int j = valid ? p.nbr[i * k + jn] : 0;
         {
-            float rv[32];
+            float rv[16];
             if (valid) {
                 const float rx = p.pos[i * p.ldpos + 0] - p.pos2[(int64_t)j * p.ldpos2 + 0];
                 const float ry = p.pos[i * p.ldpos + 1] - p.pos2[(int64_t)j * p.ldpos2 + 1];
                 const float rz = p.pos[i * p.ldpos + 2] - p.pos2[(int64_t)j * p.ldpos2 + 2];
 #pragma unroll
-                for (int t = 0; t < 32; ++t) {
+                for (int e = 0; e < 16; ++e) {
+                    const int t = half * 16 + e;
                     const float h = fmaf(p.wp1[t * 3 + 2], rz, fmaf(p.wp1[t * 3 + 1], ry, fmaf(p.wp1[t * 3 + 0], rx, p.bp1[t])));
-                    rv[t] = fmaxf(h, 0.f);
+                    rv[e] = fmaxf(h, 0.f);
                 }
             } else {
 #pragma unroll
-                for (int t = 0; t < 32; ++t) rv[t] = 0.f;
+                for (int e = 0; e < 16; ++e) rv[e] = 0.f;
             }
-            store_a_row(smem + OFF_R, smem + OFF_R + R_BYTES, r, rv);
+            store_a_half_row(smem + OFF_R, smem + OFF_R + R_BYTES, r, half, rv);
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(R_READY));
         }
-        const float* qrow = p.qa + (valid ? i : 0) * 2 * d;
-        const float* krow = p.ka + (int64_t)j * 2 * d;
-        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-        float qk[32];
+        const float* qrow = p.qa + (valid ? i : 0) * 2 * d + half * 16;
+        const float* krow = p.ka + (int64_t)j * 2 * d + half * 16;
+        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        // Qa_i - Ka_j slice of the current chunk; the next chunk's slices are requested one
+        // iteration ahead and folded into `qk` at the end of the iteration (rows of padding
+        // queries compute finite garbage that nothing reads).
+        float qk[16];
+        float4 qn[4], kn[4];
 #pragma unroll
-        for (int e = 0; e < 32; e += 4) {
-            const float4 a = *reinterpret_cast<const float4*>(qrow + e);
-            const float4 b = *reinterpret_cast<const float4*>(krow + e);
-            qk[e] = a.x - b.x; qk[e + 1] = a.y - b.y; qk[e + 2] = a.z - b.z; qk[e + 3] = a.w - b.w;
+        for (int e = 0; e < 4; ++e) {
+            qn[e] = *reinterpret_cast<const float4*>(qrow + 4 * e);
+            kn[e] = *reinterpret_cast<const float4*>(krow + 4 * e);
         }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            qk[4 * e] = qn[e].x - kn[e].x; qk[4 * e + 1] = qn[e].y - kn[e].y;
+            qk[4 * e + 2] = qn[e].z - kn[e].z; qk[4 * e + 3] = qn[e].w - kn[e].w;
+        }
+        const bool dbg = (blockIdx.x == gridDim.x / 2) && threadIdx.x == 0;
+        if (dbg) g_dbg[0] = clock64();
         for (int c = 0; c < NC; ++c) {
-            const int b = c & 1;
-            const uint32_t use = (uint32_t)(c >> 1);
-            mbar_wait(BAR(ACC1_FULL + b), use & 1u);
-            tc_fence_after();
-            uint32_t acc[32];
-            tmem_ld16_nowait(tmem_base + lane_base + ACC1_COL + b * 32, acc);
-            tmem_ld16_nowait(tmem_base + lane_base + ACC1_COL + b * 32 + 16, acc + 16);
-            tmem_ld_wait();
-            float h[32];
+            const int b = c % NBUF;
+            const uint32_t use = (uint32_t)(c / NBUF);
+            if (c + 1 < NC) {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) h[e] = valid ? fmaxf(__uint_as_float(acc[e]) + qk[e], 0.f) : 0.f;
-            if (c + 1 < NC) {   // gather the next chunk's Qa_i - Ka_j slice while this one is stored
-#pragma unroll
-                for (int e = 0; e < 32; e += 4) {
-                    const float4 a = *reinterpret_cast<const float4*>(qrow + (c + 1) * HC + e);
-                    const float4 bb = *reinterpret_cast<const float4*>(krow + (c + 1) * HC + e);
-                    qk[e] = a.x - bb.x; qk[e + 1] = a.y - bb.y; qk[e + 2] = a.z - bb.z; qk[e + 3] = a.w - bb.w;
+                for (int e = 0; e < 4; ++e) {
+                    qn[e] = *reinterpret_cast<const float4*>(qrow + (c + 1) * HC + 4 * e);
+                    kn[e] = *reinterpret_cast<const float4*>(krow + (c + 1) * HC + 4 * e);
                 }
             }
-            mbar_wait(BAR(A2_EMPTY + b), (use & 1u) ^ 1u);     // MMA2 of chunk c-2 has released the buffer
+            mbar_wait(BAR(ACC1_FULL + b), use & 1u);
+            tc_fence_after();
+            uint32_t acc[16];
+            tmem_ld16_nowait(taddr + ACC1_COL + b * 32 + half * 16, acc);
+            tmem_ld_wait();
+            float h[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) h[e] = fmaxf(__uint_as_float(acc[e]) + qk[e], 0.f);
+            mbar_wait(BAR(A2_EMPTY + b), (use & 1u) ^ 1u);     // MMA2 of chunk c-NBUF has released the buffer
             uint8_t* a2 = smem + OFF_A2 + b * 2 * R_BYTES;
-            store_a_row(a2, a2 + R_BYTES, r, h);
+            store_a_half_row(a2, a2 + R_BYTES, r, half, h);
             fence_proxy_async_smem();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(A2_FULL + b));
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                qk[4 * e] = qn[e].x - kn[e].x; qk[4 * e + 1] = qn[e].y - kn[e].y;
+                qk[4 * e + 2] = qn[e].z - kn[e].z; qk[4 * e + 3] = qn[e].w - kn[e].w;
+            }
         }
         // ------------------------------------------------ softmax / aggregation epilogue
+        if (dbg) g_dbg[1] = clock64();
         mbar_wait(BAR(ACC2_FULL), 0);
         tc_fence_after();
-        float* stg_l = reinterpret_cast<float*>(smem + OFF_W + wstage);          // stage 1 is free now
-        float* stg_v = stg_l + BM * STG_LD;
-        const float* vrow = p.vtab + (int64_t)j * d;
-        const int items = p.tq * 32;
+        if (dbg) g_dbg[2] = clock64();
+        // Staging tiles [row][33] (padding: conflict-free row-wise stores and column-wise loads with
+        // immediate offsets only): buffer 0 over the idle hidden buffers / Wc ring, buffer 1 over the
+        // idle W stage 1 (W_p2 sits in stage 0).
+        const float* vrow = p.vtab + (int64_t)j * d + half * 16;
+        const float* brow = p.bp2 + half * 16;
+        float4 vv[4], bb[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            vv[e] = *reinterpret_cast<const float4*>(vrow + 4 * e);
+            bb[e] = *reinterpret_cast<const float4*>(brow + 4 * e);
+        }
         for (int cc = 0; cc < ND; ++cc) {
             const int g = NC + cc;
-            const int b = g & 1;
-            const uint32_t use = (uint32_t)(g >> 1);
+            const int b = g % NBUF;
+            const uint32_t use = (uint32_t)(g / NBUF);
+            float* stg_l = reinterpret_cast<float*>((cc & 1) ? smem + OFF_W + w2 : smem + OFF_A2);
+            float* stg_v = stg_l + BM * STG_LD;
             mbar_wait(BAR(ACC1_FULL + b), use & 1u);
             tc_fence_after();
-            uint32_t dl[32], lg[32];
-            tmem_ld16_nowait(tmem_base + lane_base + ACC1_COL + b * 32, dl);
-            tmem_ld16_nowait(tmem_base + lane_base + ACC1_COL + b * 32 + 16, dl + 16);
-            tmem_ld16_nowait(tmem_base + lane_base + cc * 32, lg);
-            tmem_ld16_nowait(tmem_base + lane_base + cc * 32 + 16, lg + 16);
+            uint32_t dl[16], lg[16];
+            tmem_ld16_nowait(taddr + ACC1_COL + b * 32 + half * 16, dl);
+            tmem_ld16_nowait(taddr + cc * 32 + half * 16, lg);
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(A2_FULL + b));      // acc1[b] drained
+            float* sl = stg_l + r * STG_LD + half * 16;
+            float* sv = stg_v + r * STG_LD + half * 16;
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-                const int ch = cc * 32 + e;
-                const float val = valid ? (__uint_as_float(dl[e]) + p.bp2[ch] + vrow[ch]) : 0.f;
-                stg_l[r * STG_LD + e] = __uint_as_float(lg[e]);
-                stg_v[r * STG_LD + e] = val;
+            for (int e = 0; e < 4; ++e) {
+                sl[4 * e + 0] = __uint_as_float(lg[4 * e + 0]) * p.scale_log2;
+                sl[4 * e + 1] = __uint_as_float(lg[4 * e + 1]) * p.scale_log2;
+                sl[4 * e + 2] = __uint_as_float(lg[4 * e + 2]) * p.scale_log2;
+                sl[4 * e + 3] = __uint_as_float(lg[4 * e + 3]) * p.scale_log2;
+                sv[4 * e + 0] = __uint_as_float(dl[4 * e + 0]) + (vv[e].x + bb[e].x);
+                sv[4 * e + 1] = __uint_as_float(dl[4 * e + 1]) + (vv[e].y + bb[e].y);
+                sv[4 * e + 2] = __uint_as_float(dl[4 * e + 2]) + (vv[e].z + bb[e].z);
+                sv[4 * e + 3] = __uint_as_float(dl[4 * e + 3]) + (vv[e].w + bb[e].w);
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            for (int it = r; it < items; it += BM) {
-                const int q = it >> 5, ch = it & 31;
-                const int64_t gi = (int64_t)blockIdx.x * p.tq + q;
-                if (gi < p.n) {
-                    float mx = -3.4e38f;
-                    for (int jj = 0; jj < k; ++jj) mx = fmaxf(mx, stg_l[(q * k + jj) * STG_LD + ch] * p.inv_sqrt_d);
-                    float den = 0.f, num = 0.f;
-                    for (int jj = 0; jj < k; ++jj) {
-                        const float w = expf(stg_l[(q * k + jj) * STG_LD + ch] * p.inv_sqrt_d - mx);
-                        den += w;
-                        num = fmaf(w, stg_v[(q * k + jj) * STG_LD + ch], num);
-                    }
-                    p.out[gi * d + cc * 32 + ch] = num / den;
+            if (cc + 1 < ND) {   // next chunk's V / bias slices: in flight during the barrier and the reduce
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    vv[e] = *reinterpret_cast<const float4*>(vrow + (cc + 1) * 32 + 4 * e);
+                    bb[e] = *reinterpret_cast<const float4*>(brow + (cc + 1) * 32 + 4 * e);
                 }
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            // one barrier per chunk: staging buffers alternate, so the next chunk's stores cannot
+            // overtake this chunk's reduce (they are separated by the next barrier)
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            // lane = channel inside the chunk; the warp that takes two queries rotates with cc
+            for (int q = (warp + cc) & 7; q < p.tq; q += ROW_WARPS) {
+                const int64_t gi = q0 + q;
+                if (gi < p.n) {
+                    const float* lq = stg_l + (q * k) * STG_LD + lane;
+                    const float* vq = stg_v + (q * k) * STG_LD + lane;
+                    float num, den;
+                    if (KT) {
+                        float lgt[KT ? KT : 1];
+                        float mx = -3.4e38f;
+#pragma unroll
+                        for (int jj = 0; jj < KT; ++jj) {
+                            lgt[jj] = lq[jj * STG_LD];
+                            mx = fmaxf(mx, lgt[jj]);
+                        }
+                        den = 0.f; num = 0.f;
+#pragma unroll
+                        for (int jj = 0; jj < KT; ++jj) {
+                            const float w = ex2_approx(lgt[jj] - mx);
+                            den += w;
+                            num = fmaf(w, vq[jj * STG_LD], num);
+                        }
+                    } else {
+                        float mx = -3.4e38f;
+                        for (int jj = 0; jj < k; ++jj) mx = fmaxf(mx, lq[jj * STG_LD]);
+                        den = 0.f; num = 0.f;
+                        for (int jj = 0; jj < k; ++jj) {
+                            const float w = ex2_approx(lq[jj * STG_LD] - mx);
+                            den += w;
+                            num = fmaf(w, vq[jj * STG_LD], num);
+                        }
+                    }
+                    p.out[gi * d + cc * 32 + lane] = __fdividef(num, den);
+                }
+            }
         }
+        if (dbg) g_dbg[3] = clock64();
         tc_fence_before();
-    } else if (warp == 4) {
+    } else if (warp == ROW_WARPS) {
         // ================================================================== weight stream
         if (lane == 0) {
+            auto load_wc = [&](int c) {
+                const int s = c % WC_STAGES;
+                const uint32_t use = (uint32_t)(c / WC_STAGES);
+                mbar_wait(BAR(WC_EMPTY + s), (use & 1u) ^ 1u);
+                mbar_arrive_expect_tx(BAR(WC_FULL + s), 2 * WC_BYTES);
+                bulk_g2s(smem_base + OFF_WC + s * 2 * WC_BYTES, p.wmain + (size_t)c * wpacked, 2 * WC_BYTES, BAR(WC_FULL + s));
+            };
+            load_wc(0);
+            if (NC > 1) load_wc(1);
             for (int c = 0; c < NC; ++c) {
+                if (c + 2 < NC) load_wc(c + 2);              // the Wc ring runs ahead of the W_a2 ring
                 const int s = c & 1;
                 const uint32_t use = (uint32_t)(c >> 1);
                 mbar_wait(BAR(W_EMPTY + s), (use & 1u) ^ 1u);
-                mbar_arrive_expect_tx(BAR(W_FULL + s), (uint32_t)wstage);
-                bulk_g2s(smem_base + OFF_W + s * wstage, p.wmain + (size_t)c * wstage, (uint32_t)wstage, BAR(W_FULL + s));
+                mbar_arrive_expect_tx(BAR(W_FULL + s), (uint32_t)w2);
+                bulk_g2s(smem_base + OFF_W + s * w2, p.wmain + (size_t)c * wpacked + 2 * WC_BYTES, (uint32_t)w2, BAR(W_FULL + s));
             }
-            // W_p2 image into stage 0 for the delta contraction (NC is even, so this is use NC/2 of stage 0)
+            // W_p2 image into W stage 0 for the delta contraction (NC is even: this is use NC/2 of stage 0)
             const uint32_t use = (uint32_t)(NC >> 1);
             mbar_wait(BAR(W_EMPTY + 0), (use & 1u) ^ 1u);
             mbar_arrive_expect_tx(BAR(W_FULL + 0), (uint32_t)(2 * d * 64));
@@ -313,87 +423,114 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fused_kernel(const Params p) 
         }
     } else {
         // ================================================================== MMA issuer
+        // Shared-memory descriptors are loop invariant per (buffer, k-step, hi/lo, n-tile); the
+        // addresses differ only in the 14-bit start field, so every descriptor is a constant
+        // base plus a small per-buffer offset.
         if (lane == 0) {
             const uint32_t idesc32 = umma_idesc(32), idescN = umma_idesc(dn);
-            const uint32_t r_hi = smem_base + OFF_R, r_lo = r_hi + R_BYTES;
-            const uint32_t lbo_a = BM * 16;
+            const uint32_t lbo_a = BM * 16, lbo_b = (uint32_t)d * 16;
             const int split = p.split;
-            // acc1[buf] = r . B^T with B a (32 x 32) K-major image pair at b_hi / b_lo (row pitch lbo_b)
-            auto mma_k32_n32 = [&](uint32_t b_hi, uint32_t b_lo, uint32_t lbo_b, int buf) {
-                const uint32_t dcol = tmem_base + ACC1_COL + buf * 32;
+            uint64_t dr_hi[2], dr_lo[2];
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+                dr_hi[ks] = umma_desc(smem_base + OFF_R + ks * 2 * lbo_a, lbo_a, 128);
+                dr_lo[ks] = umma_desc(smem_base + OFF_R + R_BYTES + ks * 2 * lbo_a, lbo_a, 128);
+            }
+            const uint64_t dc0 = umma_desc(smem_base + OFF_WC, 512, 128);          // Wc ring slot 0, hi, ks 0
+            const uint64_t da0 = umma_desc(smem_base + OFF_A2, lbo_a, 128);        // A2 buffer 0, hi, ks 0
+            const uint64_t dw0 = umma_desc(smem_base + OFF_W, lbo_b, 128);         // W stage 0, hi, n-tile 0, ks 0
+            // acc1[c % NBUF] = r . Wc[c]^T  (K = 32, N = 32)
+            auto mma1 = [&](int c) {
+                const uint32_t dcol = tmem_base + ACC1_COL + (c % NBUF) * 32;
+                const uint64_t base = dc0 + (uint64_t)(((c % WC_STAGES) * 2 * WC_BYTES) >> 4);
 #pragma unroll
                 for (int ks = 0; ks < 2; ++ks) {
-                    const uint64_t da_hi = umma_desc(r_hi + ks * 2 * lbo_a, lbo_a, 128);
-                    const uint64_t db_hi = umma_desc(b_hi + ks * 2 * lbo_b, lbo_b, 128);
-                    umma_f16(dcol, da_hi, db_hi, idesc32, ks ? 1u : 0u);
+                    const uint64_t b_hi = base + (uint64_t)((ks * 2 * 512) >> 4);
+                    const uint64_t b_lo = b_hi + (uint64_t)(WC_BYTES >> 4);
+                    umma_f16(dcol, dr_hi[ks], b_hi, idesc32, ks ? 1u : 0u);
                     if (split) {
-                        const uint64_t da_lo = umma_desc(r_lo + ks * 2 * lbo_a, lbo_a, 128);
-                        const uint64_t db_lo = umma_desc(b_lo + ks * 2 * lbo_b, lbo_b, 128);
-                        umma_f16(dcol, da_lo, db_hi, idesc32, 1u);
-                        umma_f16(dcol, da_hi, db_lo, idesc32, 1u);
+                        umma_f16(dcol, dr_lo[ks], b_hi, idesc32, 1u);
+                        umma_f16(dcol, dr_hi[ks], b_lo, idesc32, 1u);
                     }
                 }
             };
-            mbar_wait(BAR(R_READY), 0);
-            tc_fence_after();
-            mbar_wait(BAR(W_FULL + 0), 0);
-            tc_fence_after();
-            mma_k32_n32(smem_base + OFF_W, smem_base + OFF_W + WC_BYTES, 32 * 16, 0);
-            umma_commit(BAR(ACC1_FULL + 0));
-            for (int c = 0; c < NC; ++c) {
-                const int s = c & 1;
-                const uint32_t use = (uint32_t)(c >> 1);
-                if (c + 1 < NC) {
-                    const int s1 = (c + 1) & 1;
-                    mbar_wait(BAR(W_FULL + s1), (uint32_t)((c + 1) >> 1) & 1u);
-                    tc_fence_after();
-                    const uint32_t wb = smem_base + OFF_W + s1 * wstage;
-                    mma_k32_n32(wb, wb + WC_BYTES, 32 * 16, s1);
-                    umma_commit(BAR(ACC1_FULL + s1));
-                }
-                mbar_wait(BAR(A2_FULL + s), use & 1u);
-                tc_fence_after();
-                const uint32_t a_hi = smem_base + OFF_A2 + s * 2 * R_BYTES, a_lo = a_hi + R_BYTES;
-                const uint32_t w_hi = smem_base + OFF_W + s * wstage + 2 * WC_BYTES, w_lo = w_hi + d * 64;
-                const uint32_t lbo_b = (uint32_t)d * 16;
+            // logits += hidden[c % NBUF] . W_a2[c]^T  (K = 32, N = dn per n-tile)
+            auto mma2 = [&](int c) {
+                const uint64_t abase = da0 + (uint64_t)(((c % NBUF) * 2 * R_BYTES) >> 4);
+                const uint64_t wbase = dw0 + (uint64_t)(((c & 1) * w2) >> 4);
                 for (int t = 0; t < ntile; ++t) {
                     const uint32_t dcol = tmem_base + t * dn;
-                    const uint32_t boff = (uint32_t)(t * dn / 8) * 128;
+                    const uint64_t wt = wbase + (uint64_t)(((t * dn / 8) * 128) >> 4);
 #pragma unroll
                     for (int ks = 0; ks < 2; ++ks) {
-                        const uint64_t da_hi = umma_desc(a_hi + ks * 2 * lbo_a, lbo_a, 128);
-                        const uint64_t db_hi = umma_desc(w_hi + boff + ks * 2 * lbo_b, lbo_b, 128);
-                        umma_f16(dcol, da_hi, db_hi, idescN, (c | ks) ? 1u : 0u);
+                        const uint64_t a_hi = abase + (uint64_t)((ks * 2 * lbo_a) >> 4);
+                        const uint64_t a_lo = a_hi + (uint64_t)(R_BYTES >> 4);
+                        const uint64_t w_hi = wt + (uint64_t)((ks * 2 * lbo_b) >> 4);
+                        const uint64_t w_lo = w_hi + (uint64_t)((d * 64) >> 4);
+                        umma_f16(dcol, a_hi, w_hi, idescN, (c | ks) ? 1u : 0u);
                         if (split) {
-                            const uint64_t da_lo = umma_desc(a_lo + ks * 2 * lbo_a, lbo_a, 128);
-                            const uint64_t db_lo = umma_desc(w_lo + boff + ks * 2 * lbo_b, lbo_b, 128);
-                            umma_f16(dcol, da_lo, db_hi, idescN, 1u);
-                            umma_f16(dcol, da_hi, db_lo, idescN, 1u);
+                            umma_f16(dcol, a_lo, w_hi, idescN, 1u);
+                            umma_f16(dcol, a_hi, w_lo, idescN, 1u);
                         }
                     }
                 }
-                umma_commit(BAR(W_EMPTY + s));
-                umma_commit(BAR(A2_EMPTY + s));
+            };
+            auto issue_mma1 = [&](int c) {
+                mbar_wait(BAR(WC_FULL + c % WC_STAGES), (uint32_t)(c / WC_STAGES) & 1u);
+                tc_fence_after();
+                mma1(c);
+                umma_commit(BAR(ACC1_FULL + c % NBUF));
+                umma_commit(BAR(WC_EMPTY + c % WC_STAGES));
+            };
+            mbar_wait(BAR(R_READY), 0);
+            tc_fence_after();
+            issue_mma1(0);
+            if (NC > 1) issue_mma1(1);
+            for (int c = 0; c < NC; ++c) {
+                // acc1[(c+2) % 3] was last used by chunk c-1, drained before MMA2(c-1) was issued
+                if (c + 2 < NC) issue_mma1(c + 2);
+                mbar_wait(BAR(A2_FULL + c % NBUF), (uint32_t)(c / NBUF) & 1u);
+                mbar_wait(BAR(W_FULL + (c & 1)), (uint32_t)(c >> 1) & 1u);
+                tc_fence_after();
+                mma2(c);
+                umma_commit(BAR(W_EMPTY + (c & 1)));
+                umma_commit(BAR(A2_EMPTY + c % NBUF));
             }
             umma_commit(BAR(ACC2_FULL));
-            // delta chunks: acc1[g & 1] = r . W_p2[cc*32 .. +32]^T
+            // delta chunks: acc1[g % 3] = r . W_p2[cc*32 .. +32]^T   (g = NC + cc continues the buffer ring)
             mbar_wait(BAR(W_FULL + 0), (uint32_t)(NC >> 1) & 1u);
             tc_fence_after();
-            const uint32_t p_hi = smem_base + OFF_W, p_lo = p_hi + d * 64;
+            const uint64_t dp_hi0 = umma_desc(smem_base + OFF_W, lbo_b, 128);
+            const uint64_t dp_hi1 = umma_desc(smem_base + OFF_W + 2 * lbo_b, lbo_b, 128);
+            const uint64_t dp_lo0 = umma_desc(smem_base + OFF_W + d * 64, lbo_b, 128);
+            const uint64_t dp_lo1 = umma_desc(smem_base + OFF_W + d * 64 + 2 * lbo_b, lbo_b, 128);
             for (int cc = 0; cc < ND; ++cc) {
                 const int g = NC + cc;
-                const int b = g & 1;
-                const uint32_t use = (uint32_t)(g >> 1);
-                mbar_wait(BAR(A2_FULL + b), (use - 1u) & 1u);   // previous contents of acc1[b] were drained
-                tc_fence_after();
-                mma_k32_n32(p_hi + cc * 512, p_lo + cc * 512, (uint32_t)d * 16, b);
+                const int b = g % NBUF;
+                const uint32_t use = (uint32_t)(g / NBUF);
+                if (use > 0) {                                   // previous contents of acc1[b] were drained
+                    mbar_wait(BAR(A2_FULL + b), (use - 1u) & 1u);
+                    tc_fence_after();
+                }
+                const uint32_t dcol = tmem_base + ACC1_COL + b * 32;
+                const uint64_t adv = (uint64_t)(cc * 512 >> 4);  // 32 rows further down the W_p2 image
+                umma_f16(dcol, dr_hi[0], dp_hi0 + adv, idesc32, 0u);
+                if (split) {
+                    umma_f16(dcol, dr_lo[0], dp_hi0 + adv, idesc32, 1u);
+                    umma_f16(dcol, dr_hi[0], dp_lo0 + adv, idesc32, 1u);
+                }
+                umma_f16(dcol, dr_hi[1], dp_hi1 + adv, idesc32, 1u);
+                if (split) {
+                    umma_f16(dcol, dr_lo[1], dp_hi1 + adv, idesc32, 1u);
+                    umma_f16(dcol, dr_hi[1], dp_lo1 + adv, idesc32, 1u);
+                }
                 umma_commit(BAR(ACC1_FULL + b));
             }
         }
     }
 #undef BAR
     __syncthreads();
-    if (warp == 4) {
+    if (warp == ROW_WARPS) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
@@ -446,7 +583,7 @@ __global__ void fused_pack_kernel(const float* __restrict__ wc, const float* __r
 }  // namespace fa
 
 bool attn_fused_supported(int d, int k) {
-    if (d % 32 != 0 || d < 256 || d > 416 || k < 1 || k > O4D_MAX_K) return false;
+    if (d % 32 != 0 || d < 288 || d > 416 || k < 8 || k > O4D_MAX_K) return false;  // k >= 8: at most 16 queries per tile
     const int dn = d > 256 ? d / 2 : d;
     return dn % 16 == 0 && dn <= 256 && fa::smem_bytes(d) <= 227 * 1024;
 }
@@ -472,7 +609,10 @@ int attn_fused_launch(const PtBlockParams& P, const AttnTables& T, const float* 
     O4D_REQUIRE(attn_fused_supported(d, k) && T.fused, "fused attention: unsupported shape or missing weights");
     static bool attr_done = false;
     if (!attr_done) {
-        O4D_CUDA(cudaFuncSetAttribute(fa::attn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        O4D_CUDA(cudaFuncSetAttribute(fa::attn_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        O4D_CUDA(cudaFuncSetAttribute(fa::attn_fused_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        O4D_CUDA(cudaFuncSetAttribute(fa::attn_fused_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        O4D_CUDA(cudaFuncSetAttribute(fa::attn_fused_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_done = true;
     }
     const int NC = 2 * d / fa::HC;
@@ -484,14 +624,25 @@ int attn_fused_launch(const PtBlockParams& P, const AttnTables& T, const float* 
     p.wp2 = (const uint8_t*)T.fused + align_up((size_t)NC * fa::wstage_bytes(d), 256);
     p.out = out;
     p.n = n; p.d = d; p.k = k; p.tq = fa::BM / k; p.split = (precision == 1) ? 1 : 0;
-    p.inv_sqrt_d = (float)(1.0 / sqrt((double)d));
+    p.scale_log2 = (float)(1.4426950408889634 / sqrt((double)d));
     const int64_t tiles = cdiv(n, p.tq);
     // algorithmic flops of what this launch replaces (reference formulation): per pair 2*(3*32 + 32*d) +
     // 2*d*2d*2, softmax/aggregate ~6d
     ProfScope prof(PROF_FUSED, (double)n * k * (2.0 * (3 * 32 + 32.0 * d) + 8.0 * d * d + 6.0 * d), st);
-    fa::attn_fused_kernel<<<(unsigned)tiles, fa::THREADS, fa::smem_bytes(d), st>>>(p);
+    const unsigned grid = (unsigned)tiles;
+    const size_t smem = fa::smem_bytes(d);
+    switch (k) {
+        case 12: fa::attn_fused_kernel<12><<<grid, fa::THREADS, smem, st>>>(p); break;
+        case 14: fa::attn_fused_kernel<14><<<grid, fa::THREADS, smem, st>>>(p); break;
+        case 16: fa::attn_fused_kernel<16><<<grid, fa::THREADS, smem, st>>>(p); break;
+        default: fa::attn_fused_kernel<0><<<grid, fa::THREADS, smem, st>>>(p); break;
+    }
     O4D_LAUNCH_CHECK();
     return 0;
 }
 
 }  // namespace o4d
+
+extern "C" int o4d_debug_read(long long* out16) {
+    return (int)cudaMemcpyFromSymbol(out16, o4d::fa::g_dbg, sizeof(long long) * 16);
+}

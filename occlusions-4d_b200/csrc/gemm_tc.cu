@@ -198,40 +198,50 @@ linear_tc_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda, 
 
     if (warp < 4) {
         // ------------------------------------------------------------ A producers
+        // The fp32 -> bf16 hi/lo conversion needs the data in registers, so the global loads of
+        // chunk c+1 are issued BEFORE chunk c is converted and stored: their latency hides behind
+        // the stage wait, the conversion and the shared-memory stores of the current chunk.
         const bool relu_in = flags & O4D_RELU_IN;
         const int kc = lane >> 3, rr = lane & 7;
-        for (int c = 0; c < nchunks; ++c) {
-            const int s = c % STAGES;
-            const uint32_t ph = (uint32_t)(c / STAGES) & 1u;
-            mbar_wait(empty0 + 8 * s, ph ^ 1u);
-            uint8_t* a_hi = smem + s * STAGE_BYTES;
-            uint8_t* a_lo = a_hi + A_HALF_BYTES;
+        auto load_chunk = [&](int c, float (&v)[4][8]) {
             const int gk = c * BK + kc * 8;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-                const int rg = warp * 4 + g;                  // 8-row group inside the 128-row tile
-                const int64_t grow = row0 + rg * 8 + rr;
-                float v[8];
+                const int64_t grow = row0 + (warp * 4 + g) * 8 + rr;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = 0.f;
+                for (int i = 0; i < 8; ++i) v[g][i] = 0.f;
                 if (grow < rows) {
                     const float* src = A + grow * lda + gk;
                     if (gk + 8 <= k && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
                         const float4 p0 = *reinterpret_cast<const float4*>(src);
                         const float4 p1 = *reinterpret_cast<const float4*>(src + 4);
-                        v[0] = p0.x; v[1] = p0.y; v[2] = p0.z; v[3] = p0.w;
-                        v[4] = p1.x; v[5] = p1.y; v[6] = p1.z; v[7] = p1.w;
+                        v[g][0] = p0.x; v[g][1] = p0.y; v[g][2] = p0.z; v[g][3] = p0.w;
+                        v[g][4] = p1.x; v[g][5] = p1.y; v[g][6] = p1.z; v[g][7] = p1.w;
                     } else {
 #pragma unroll
                         for (int i = 0; i < 8; ++i)
-                            if (gk + i < k) v[i] = src[i];
+                            if (gk + i < k) v[g][i] = src[i];
                     }
                 }
+            }
+        };
+        float cur[4][8], nxt[4][8];
+        load_chunk(0, cur);
+        for (int c = 0; c < nchunks; ++c) {
+            const int s = c % STAGES;
+            const uint32_t ph = (uint32_t)(c / STAGES) & 1u;
+            if (c + 1 < nchunks) load_chunk(c + 1, nxt);
+            mbar_wait(empty0 + 8 * s, ph ^ 1u);
+            uint8_t* a_hi = smem + s * STAGE_BYTES;
+            uint8_t* a_lo = a_hi + A_HALF_BYTES;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int rg = warp * 4 + g;                  // 8-row group inside the 128-row tile
                 __align__(16) __nv_bfloat16 h[8];
                 __align__(16) __nv_bfloat16 l[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    float x = relu_in ? fmaxf(v[i], 0.f) : v[i];
+                    float x = relu_in ? fmaxf(cur[g][i], 0.f) : cur[g][i];
                     split_bf16(x, h[i], l[i]);
                 }
                 const int off = kc * (BM * 16) + rg * 128 + rr * 16;   // [kc][row group][row][16 B]
@@ -241,6 +251,10 @@ linear_tc_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda, 
             fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
             __syncwarp();
             if (lane == 0) mbar_arrive(full0 + 8 * s);
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) cur[g][i] = nxt[g][i];
         }
         // ------------------------------------------------------------ epilogue
         mbar_wait(accum_bar, 0);

@@ -117,6 +117,8 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
     lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
 
+__device__ long long g_dbg_tc[16];   // cycle stamps of one CTA (diagnostics)
+
 struct PackMeta {
     int n, k;      // logical weight shape
     int bn;        // tile width (multiple of 16, <= 256)
@@ -226,6 +228,8 @@ linear_tc_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda, 
             }
         };
         float cur[4][8], nxt[4][8];
+        const bool dbg = (blockIdx.x == gridDim.x / 2) && blockIdx.y == 0 && threadIdx.x == 0;
+        if (dbg) g_dbg_tc[0] = clock64();
         load_chunk(0, cur);
         for (int c = 0; c < nchunks; ++c) {
             const int s = c % STAGES;
@@ -257,54 +261,97 @@ linear_tc_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda, 
                 for (int i = 0; i < 8; ++i) cur[g][i] = nxt[g][i];
         }
         // ------------------------------------------------------------ epilogue
+        // TMEM hands every thread one ROW (32x32b shape); storing C that way touches 32 cache
+        // lines per instruction and made the epilogue 2x longer than the main loop.  Each warp
+        // instead transposes 32 x 32 blocks through a padded shared-memory tile (the pipeline
+        // stages are idle by now): in the write phase a lane owns one COLUMN, so every load of
+        // the residual and every store of C is one contiguous 128-byte row segment, and the loads
+        // of eight rows are issued back to back before they are consumed.
+        if (dbg) g_dbg_tc[1] = clock64();
         mbar_wait(accum_bar, 0);
         tc_fence_after();
+        if (dbg) g_dbg_tc[2] = clock64();
         const bool relu_out = flags & O4D_RELU_OUT;
-        const int64_t grow = row0 + warp * 32 + lane;
+        const int64_t warp_row0 = row0 + warp * 32;
         const int col_base = tile_n * bn;
         const uint32_t taddr_row = tmem_base + ((uint32_t)(warp * 32) << 16);
-        const float* gq = nullptr;   // row-dependent additive term (attention MLP first layer)
-        const float* gk = nullptr;
-        if (g.qa && grow < rows) {
-            const int64_t ar = g.row_offset + grow;
-            gq = g.qa + (ar / g.knbr) * m.n;
-            gk = g.ka + (int64_t)g.nbr[ar] * m.n;
-        }
-        for (int c0 = 0; c0 < bn; c0 += 16) {
-            float v[16];
-            tmem_ld16(taddr_row + (uint32_t)c0, v);     // warp-collective: every lane executes it
-            if (grow < rows) {
-                const int gc0 = col_base + c0;
-                float* dst = C + grow * ldc + gc0;
-                const float* res = R ? R + grow * ldr + gc0 : nullptr;
-                if (gc0 + 16 <= m.n) {
+        constexpr int SLD = 36;                            // staging row pitch (floats): 16-byte aligned rows, conflict-free
+        float* stg = reinterpret_cast<float*>(smem) + warp * (32 * SLD);
+        const int rows_here = (int)min((int64_t)32, rows - warp_row0);     // may be <= 0 for a ragged last tile
+        const bool vec_ok = !g.qa && (m.n % 4 == 0) && (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) &&
+                            (!R || ((ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(R) & 15) == 0))) &&
+                            (!bias || ((reinterpret_cast<uintptr_t>(bias) & 15) == 0));
+        if (vec_ok) {
+            // write phase: lane -> (row-in-group rr, 4 columns c4): one instruction covers 4 rows x 128 B
+            const int rr = lane >> 3, c4 = (lane & 7) * 4;
+            float4 resn[8];
+            auto load_res = [&](int c0) {
+                const int gc = col_base + c0 + c4;
+                const bool ok = R && c4 < min(32, bn - c0) && gc < m.n;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        float x = v[i] + (bias ? bias[gc0 + i] : 0.f);
-                        if (gq) x += gq[gc0 + i] - gk[gc0 + i];
-                        if (relu_out) x = fmaxf(x, 0.f);
-                        if (res) x += res[i];
-                        v[i] = x;
+                for (int it = 0; it < 8; ++it) {
+                    const int row = it * 4 + rr;
+                    resn[it] = (ok && row < rows_here) ? *reinterpret_cast<const float4*>(R + (warp_row0 + row) * ldr + gc)
+                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            };
+            load_res(0);
+            for (int c0 = 0; c0 < bn; c0 += 32) {
+                const int width = min(32, bn - c0);
+                float4 res[8];
+#pragma unroll
+                for (int it = 0; it < 8; ++it) res[it] = resn[it];
+                if (c0 + 32 < bn) load_res(c0 + 32);
+                float v[32];
+                tmem_ld16(taddr_row + (uint32_t)c0, v);
+                if (width > 16) tmem_ld16(taddr_row + (uint32_t)(c0 + 16), v + 16);
+#pragma unroll
+                for (int i = 0; i < 32; i += 4)
+                    if (i < width) *reinterpret_cast<float4*>(stg + lane * SLD + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                __syncwarp();
+                const int gc = col_base + c0 + c4;
+                if (c4 < width && gc < m.n) {
+                    const float4 bv = bias ? *reinterpret_cast<const float4*>(bias + gc) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int row = it * 4 + rr;
+                        if (row < rows_here) {
+                            float4 x = *reinterpret_cast<const float4*>(stg + row * SLD + c4);
+                            x.x += bv.x; x.y += bv.y; x.z += bv.z; x.w += bv.w;
+                            if (relu_out) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+                            x.x += res[it].x; x.y += res[it].y; x.z += res[it].z; x.w += res[it].w;
+                            *reinterpret_cast<float4*>(C + (warp_row0 + row) * ldc + gc) = x;
+                        }
                     }
-                    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-#pragma unroll
-                        for (int i = 0; i < 16; i += 4)
-                            *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) dst[i] = v[i];
-                    }
-                } else {
+                }
+                __syncwarp();
+            }
+        } else {
+            // generic path (unaligned views, n % 4 != 0, row-gather epilogue): one row per thread
+            const int64_t grow = warp_row0 + lane;
+            const float* gq = nullptr;
+            const float* gk = nullptr;
+            if (g.qa && grow < rows) {
+                const int64_t ar = g.row_offset + grow;
+                gq = g.qa + (ar / g.knbr) * m.n;
+                gk = g.ka + (int64_t)g.nbr[ar] * m.n;
+            }
+            for (int c0 = 0; c0 < bn; c0 += 16) {
+                float v[16];
+                tmem_ld16(taddr_row + (uint32_t)c0, v);
+                if (grow < rows) {
+                    const int gc0 = col_base + c0;
                     for (int i = 0; i < 16 && gc0 + i < m.n; ++i) {
                         float x = v[i] + (bias ? bias[gc0 + i] : 0.f);
                         if (gq) x += gq[gc0 + i] - gk[gc0 + i];
                         if (relu_out) x = fmaxf(x, 0.f);
-                        if (res) x += res[i];
-                        dst[i] = x;
+                        if (R) x += R[grow * ldr + gc0 + i];
+                        C[grow * ldc + gc0 + i] = x;
                     }
                 }
             }
         }
+        if (dbg) g_dbg_tc[3] = clock64();
         tc_fence_before();
     } else if (warp == 4) {
         // ------------------------------------------------------------ weight slabs via the TMA engine
@@ -409,3 +456,6 @@ int linear_tc_launch(const float* A, int64_t rows, int64_t k, int64_t lda, const
 }  // namespace o4d
 
 extern "C" int o4d_has_tcgen05(void) { return 1; }
+extern "C" int o4d_debug_read_tc(long long* out16) {
+    return (int)cudaMemcpyFromSymbol(out16, o4d::tc::g_dbg_tc, sizeof(long long) * 16);
+}

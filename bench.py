@@ -224,12 +224,12 @@ def run_o4d(args):
         gathered = torch.empty((world * nq, d_out), dtype=torch.float32, device=dev) if world > 1 else None
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-        def step_device():
+        def step_device(comm=True):
             flush.fill_(1)                                   # L2 flush (torch fill, not an o4d kernel)
             for s in range(0, nq, batch):
                 ops.decoder_forward(dcfg, dparams, scene, q_dev[s:s + batch], want_penult=False,
                                     out=out_dev[s:s + batch])
-            if world > 1:
+            if world > 1 and comm:
                 dist.all_gather_into_tensor(gathered, out_dev)
 
         for _ in range(args.warmup):
@@ -267,7 +267,7 @@ def run_o4d(args):
         roofline, families = None, None
         if rank == 0:
             lib.o4d_profile_enable(1)
-            step_device()
+            step_device(comm=False)                          # rank 0 only: no collective here
             torch.cuda.synchronize()
             import ctypes
             n = len(FAMILIES)
@@ -323,7 +323,7 @@ def main():
     ap.add_argument('--impl', default='o4d', choices=['o4d', 'reference'])
     ap.add_argument('--batch', type=int, default=32768, help='implicit_batch_size')
     ap.add_argument('--precision', type=int, default=None, help='0 fp32 CUDA cores, 1 tcgen05 bf16x3, 2 bf16')
-    ap.add_argument('--cpu-sample', type=int, default=16384)
+    ap.add_argument('--cpu-sample', type=int, default=196608)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -89,6 +89,14 @@ attn_softmax_agg_kernel(const float* __restrict__ logits, const float* __restric
     agg[(i0 + il) * d + c] = num / den;
 }
 
+int matmul_nn_launch(const float* A, int lda, const float* B, int ldb, const float* addvec, float* C, int p, int q, int r,
+                     cudaStream_t st) {
+    ProfScope prof(PROF_MISC, 2.0 * p * q * r, st);
+    matmul_nn_kernel<<<(unsigned)cdiv((int64_t)p * r, 256), 256, 0, st>>>(A, lda, B, ldb, addvec, C, p, q, r);
+    O4D_LAUNCH_CHECK();
+    return 0;
+}
+
 // ---- per-cloud tables: Ka = K W_a1^T, Wc = W_a1 W_p2, cvec = W_a1 b_p2 + b_a1 ------------------
 size_t attn_tables_bytes(int64_t m, int d) {
     Arena a(nullptr, 0);
@@ -165,7 +173,10 @@ int attn_core_launch(const PtBlockParams& P, const float* q, const AttnTables& T
         return O4D_E_WORKSPACE;
     }
     // Qa = W_a1 q + (W_a1 b_p2 + b_a1): the per-query part of the first attention-MLP layer
-    O4D_TRY(linear_ps_launch(P.ps, q, n, d, d, P.wa1, d, T.cvec, 2 * d, nullptr, 0, qa, 2 * d, 0, precision, st));
+    if (T.wqa)   // q is the block input x: layer1, to_q and W_a1 folded into one weight
+        O4D_TRY(linear_ps_launch(P.ps, q, n, d, d, T.wqa, d, T.bqa, 2 * d, nullptr, 0, qa, 2 * d, 0, precision, st));
+    else
+        O4D_TRY(linear_ps_launch(P.ps, q, n, d, d, P.wa1, d, T.cvec, 2 * d, nullptr, 0, qa, 2 * d, 0, precision, st));
     const float inv_sqrt_d = (float)(1.0 / sqrt((double)d));
     const bool fused = precision != 0 && T.fused != nullptr && attn_fused_supported(d, k);
     if (fused)   // everything between Qa and the aggregated output in one tcgen05 kernel

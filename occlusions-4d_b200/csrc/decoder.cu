@@ -56,6 +56,10 @@ struct SceneView {
     char* tables[O4D_MAX_BLOCKS];  // attention tables (Ka, Wc, cvec) per cross layer
     size_t tables_bytes;
     char* fused[O4D_MAX_BLOCKS];   // packed weights of the fused attention kernel (or null)
+    float* wqa[O4D_MAX_BLOCKS];    // (2H, H) = W_a1 W_q W_1         per cross layer
+    float* bqa[O4D_MAX_BLOCKS];    // (2H)    = W_a1 W_q b_1 + cvec
+    float* t1[O4D_MAX_BLOCKS];     // (H, H)  = W_q W_1 (scratch kept for the lifetime of the scene)
+    float* t1b[O4D_MAX_BLOCKS];    // (H)     = W_q b_1
     size_t pack_off;  // byte offset of the pre-packed tcgen05 weights (precision != 0)
     size_t bytes;
 };
@@ -79,6 +83,12 @@ static SceneView scene_view(const o4d_decoder_config* c, int64_t m, void* base) 
         s.fused[j] = use_fused ? a.get<char>(attn_fused_pack_bytes(c->d_hidden)) : nullptr;
     if (use_fused && base == nullptr)
         for (int j = 0; j < c->cross_attn_layers; ++j) s.fused[j] = nullptr;
+    for (int j = 0; j < c->cross_attn_layers; ++j) {
+        s.wqa[j] = a.get<float>((size_t)2 * c->d_hidden * c->d_hidden);
+        s.bqa[j] = a.get<float>((size_t)2 * c->d_hidden);
+        s.t1[j] = a.get<float>((size_t)c->d_hidden * c->d_hidden);
+        s.t1b[j] = a.get<float>((size_t)c->d_hidden);
+    }
     s.pack_off = a.off;
     a.get<char>(packed_total_bytes(c));
     s.bytes = a.off;
@@ -104,9 +114,7 @@ static void for_each_tc_weight(const o4d_decoder_config* c, const DecParams& d, 
     }
     for (int j = 0; j < c->cross_attn_layers; ++j) {
         const float* const* p = d.pt[j];
-        fn(p ? p[0] : nullptr, H, H, H);           // layer1
-        fn(p ? p[2] : nullptr, H, H, H);           // to_q
-        fn(p ? p[9] : nullptr, 2 * H, H, H);       // attn_mlp.0 (per-query part Qa)
+        fn(s ? s->wqa[j] : nullptr, 2 * H, H, H);  // W_a1 W_q W_1: block input -> Qa
         fn(p ? p[11] : nullptr, H, 2 * H, 2 * H);  // attn_mlp.2
         fn(p ? p[13] : nullptr, H, H, H);          // layer3
         fn(p ? p[7] : nullptr, H, 32, 32);         // pos_mlp.2 (delta)
@@ -160,6 +168,11 @@ int decoder_prepare(const o4d_decoder_config* c, const float* const* P, const fl
         AttnTables T;
         O4D_TRY(attn_tables_launch(pp, s.ktab[j], s.vtab[j], m, H, s.tables[j], s.tables_bytes, &T, st));
         if (s.fused[j]) O4D_TRY(attn_fused_pack_launch(T.wc, pp.wa2, pp.wp2, H, s.fused[j], st));
+        // composite input weight of the attention block (fp64 accumulation, rounded once)
+        O4D_TRY(matmul_nn_launch(pp.wq, H, pp.w1, H, nullptr, s.t1[j], H, H, H, st));
+        O4D_TRY(matmul_nn_launch(pp.wa1, H, s.t1[j], H, nullptr, s.wqa[j], 2 * H, H, H, st));
+        O4D_TRY(matmul_nn_launch(pp.wq, H, pp.b1, 1, nullptr, s.t1b[j], H, H, 1, st));
+        O4D_TRY(matmul_nn_launch(pp.wa1, H, s.t1b[j], 1, T.cvec, s.bqa[j], 2 * H, H, 1, st));
     }
     if (c->precision != 0) {
         // bf16 hi/lo shared-memory images of every weight the tcgen05 path reads
@@ -248,8 +261,6 @@ int decoder_forward(const o4d_decoder_config* c, const float* const* P, const vo
             const int j = d.use_pt[b];
             PtBlockParams pp = PtBlockParams::from(d.pt[j]);
             pp.ps = &ps;
-            O4D_TRY(linear_ps_launch(&ps, w.x, nq, H, H, pp.w1, H, pp.b1, H, nullptr, 0, w.y, H, 0, prec, st));
-            O4D_TRY(linear_ps_launch(&ps, w.y, nq, H, H, pp.wq, H, nullptr, H, nullptr, 0, w.h, H, 0, prec, st));
             AttnTables T;
             {
                 Arena ta(s.tables[j], s.tables_bytes);   // same carve-up as attn_tables_launch
@@ -258,8 +269,10 @@ int decoder_forward(const o4d_decoder_config* c, const float* const* P, const vo
                 T.cvec = ta.get<float>((size_t)2 * H);
                 T.vtab = s.vtab[j];
                 T.fused = s.fused[j];
+                T.wqa = s.wqa[j];
+                T.bqa = s.bqa[j];
             }
-            O4D_TRY(attn_core_launch(pp, w.h, T, query, c->d_in, s.abs_xyz, 3, w.idx_c, nq, H,
+            O4D_TRY(attn_core_launch(pp, w.x, T, query, c->d_in, s.abs_xyz, 3, w.idx_c, nq, H,
                                      c->cross_attn_neighbors, w.x, w.x, prec, w.sub, w.sub_bytes, st));
         }
     }

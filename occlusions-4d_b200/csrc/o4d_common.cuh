@@ -158,6 +158,10 @@ struct AttnTables {
     const float* wc;
     const float* cvec;
     const void* fused = nullptr;   // packed weight images of the fused tcgen05 kernel (attn_fused.cu) or null
+    // optional composite of everything between the block input x and Qa (decoder):
+    //   Qa = (W_a1 W_q W_1) x + (W_a1 W_q b_1 + cvec);  when set, attn_core takes x instead of q
+    const float* wqa = nullptr;
+    const float* bqa = nullptr;
 };
 bool attn_fused_supported(int d, int k);
 size_t attn_fused_pack_bytes(int d);
@@ -168,6 +172,8 @@ int attn_fused_launch(const PtBlockParams& P, const AttnTables& T, const float* 
 size_t attn_tables_bytes(int64_t m, int d);
 int attn_tables_launch(const PtBlockParams& P, const float* ktab, const float* vtab, int64_t m, int d, void* buf,
                        size_t buf_bytes, AttnTables* out, cudaStream_t st);
+int matmul_nn_launch(const float* A, int lda, const float* B, int ldb, const float* addvec, float* C, int p, int q, int r,
+                     cudaStream_t st);
 size_t attn_core_workspace_bytes(int64_t n, int d, int k);
 int attn_core_launch(const PtBlockParams& P, const float* q, const AttnTables& T, const float* pos, int64_t ldpos,
                      const float* pos2, int64_t ldpos2, const int32_t* nbr, int64_t n, int d, int k,

@@ -243,6 +243,73 @@ int o4d_decoder_run_host(const o4d_decoder_config* cfg, const float* const* para
                          float* out_host,
                          void* device_scratch, size_t device_scratch_bytes, void* stream);
 
+/* ================================================================== training path
+ * The reference trains through torch.autograd over its eager graph (train.py:282-296 ->
+ * pipeline.py:93-212 -> the forward()s above).  Here every gradient is an explicit kernel;
+ * occlusions-4d_b200/o4d/autograd.py wraps the pairs below in torch.autograd.Function so
+ * that loss.backward() in the unmodified train.py reaches them.  All gradient outputs are
+ * OVERWRITTEN (autograd accumulates), indices are int64 as everywhere at this boundary. */
+
+/* out = dy where y > 0 else 0 (ReLU backward from the layer OUTPUT; count elements). */
+int o4d_relu_backward_f32(const float* dy, const float* y, int64_t count, float* out, void* stream);
+
+/* Backward of o4d_linear_f32's  Y = pre(A) W^T + b  (flags: O4D_RELU_IN as in the forward; a
+ * forward O4D_RELU_OUT is undone by the caller with o4d_relu_backward_f32 on dY first; the
+ * residual R passes dY through unchanged).
+ *   dA (rows, k) = (dY W) * [A > 0 if RELU_IN]      dW (n, k) = dY^T pre(A)      db (n) = sum_r dY
+ * Any of dA / dW / db may be NULL.  W has leading dimension ldw (column slices of lin_z). */
+size_t o4d_linear_backward_workspace_bytes(int64_t rows, int64_t k, int64_t n);
+int o4d_linear_backward_f32(const float* A, int64_t rows, int64_t k, int64_t lda,
+                            const float* W, int64_t ldw, int64_t n,
+                            const float* dY, int64_t lddy, int flags,
+                            float* dA, int64_t ldda, float* dW, int64_t lddw, float* db,
+                            int precision, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Vector-attention core with saved activations (point_transformer_layer.py:174-179 given
+ * q = to_q(x) (n,d), ktab = to_k(x2) (m,d), vtab = to_v(x2) (m,d) and nbr (n,k) int64):
+ *   p8 = pos_mlp.0.{w,b}, pos_mlp.2.{w,b}, attn_mlp.0.{w,b}, attn_mlp.2.{w,b}
+ * forward writes agg (n,d) and fills `saved` (o4d_attn_train_saved_bytes) with r, u, relu-hidden,
+ * softmax weights and V+delta; backward consumes it and returns dq, dktab, dvtab and the eight
+ * parameter gradients dp8 (same shapes as p8). */
+size_t o4d_attn_train_saved_bytes(int64_t n, int d, int k);
+size_t o4d_attn_backward_workspace_bytes(int64_t n, int d, int k);
+int o4d_attn_forward_train(const float* const* p8, const float* q, const float* ktab, const float* vtab, int64_t m,
+                           const float* pos, int64_t ldpos, const float* pos2, int64_t ldpos2,
+                           const int64_t* nbr, int64_t n, int d, int k, int precision,
+                           float* agg_out, void* saved, size_t saved_bytes, void* stream);
+int o4d_attn_backward(const float* const* p8, const float* pos, int64_t ldpos, const float* pos2, int64_t ldpos2,
+                      const int64_t* nbr, int64_t n, int64_t m, int d, int k, int precision,
+                      const void* saved, size_t saved_bytes, const float* agg, const float* dagg,
+                      float* dq, float* dktab, float* dvtab, float* const* dp8,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* Inverse-distance feature blend, implicit.py:337-339, and its gradient w.r.t. the abstract
+ * features (distances / indices carry no gradient: coordinates are data).
+ *   idx (n,k) int64, dist (n,k), feat (m,e) ldfeat -> out (n,e);   dfeat (m,e) lddfeat. */
+int o4d_local_blend_f32(const int64_t* idx, const float* dist, const float* feat, int64_t ldfeat,
+                        int64_t n, int k, int e, float* out, void* stream);
+int o4d_local_blend_backward_f32(const int64_t* idx, const float* dist, const float* dout,
+                                 int64_t n, int k, int e, int64_t m, float* dfeat, int64_t lddfeat, void* stream);
+
+/* Neighbourhood max-pool of the down transition, modules.py:156-158, with the winning source
+ * row per (output row, channel) recorded (first maximum), and the routing of dz back to it. */
+int o4d_gather_max_f32(const float* y, int64_t ldy, const int64_t* nbr, int64_t n_out, int k, int d,
+                       float* z, int32_t* arg_out, void* stream);
+int o4d_gather_max_backward_f32(const float* dz, const int32_t* arg, int64_t n_out, int d, int64_t n_src,
+                                float* dy, int64_t lddy, void* stream);
+
+/* relu(LayerNorm(y)) of the CARLA down transition (modules.py:107-110), out of place, and its
+ * gradients (dy, dgamma, dbeta). */
+int o4d_layernorm_relu_f32(const float* y, int64_t rows, int d, const float* gamma, const float* beta,
+                           float eps, float* out, void* stream);
+int o4d_layernorm_relu_backward_f32(const float* y, const float* dout, int64_t rows, int d,
+                                    const float* gamma, const float* beta, float eps,
+                                    float* dy, float* dgamma, float* dbeta, void* stream);
+
+/* Mean over points (model.py:189) and its gradient (dmean / rows broadcast to every row). */
+int o4d_col_mean_f32(const float* x, int64_t rows, int d, float* out, void* stream);
+int o4d_col_mean_backward_f32(const float* dmean, int64_t rows, int d, float* dx, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -50,7 +50,7 @@ ProfScope::~ProfScope() {
 }  // namespace o4d
 
 extern "C" const char* o4d_last_error(void) { return o4d::g_err; }
-extern "C" int o4d_abi_version(void) { return 1; }
+extern "C" int o4d_abi_version(void) { return 2; }
 extern "C" uint64_t o4d_launch_count(void) { return o4d::g_launches.load(); }
 
 extern "C" void o4d_profile_enable(int on) {

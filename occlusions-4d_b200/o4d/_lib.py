@@ -68,6 +68,26 @@ SIGNATURES = {
     'o4d_decoder_run_host_device_bytes': (c_size, [ctypes.POINTER(DecoderConfig), c_i64, c_i64]),
     'o4d_decoder_run_host': (c_int, [ctypes.POINTER(DecoderConfig), c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_i64,
                                      c_ptr, c_ptr, c_size, c_ptr]),
+    'o4d_relu_backward_f32': (c_int, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr]),
+    'o4d_linear_backward_workspace_bytes': (c_size, [c_i64, c_i64, c_i64]),
+    'o4d_linear_backward_f32': (c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_int,
+                                        c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_int, c_ptr, c_size, c_ptr]),
+    'o4d_attn_train_saved_bytes': (c_size, [c_i64, c_int, c_int]),
+    'o4d_attn_backward_workspace_bytes': (c_size, [c_i64, c_int, c_int]),
+    'o4d_attn_forward_train': (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_ptr,
+                                       c_i64, c_int, c_int, c_int, c_ptr, c_ptr, c_size, c_ptr]),
+    'o4d_attn_backward': (c_int, [c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_i64, c_int, c_int, c_int,
+                                  c_ptr, c_size, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_size, c_ptr]),
+    'o4d_local_blend_f32': (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_int, c_int, c_ptr, c_ptr]),
+    'o4d_local_blend_backward_f32': (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_int, c_int, c_i64, c_ptr, c_i64,
+                                             c_ptr]),
+    'o4d_gather_max_f32': (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_int, c_int, c_ptr, c_ptr, c_ptr]),
+    'o4d_gather_max_backward_f32': (c_int, [c_ptr, c_ptr, c_i64, c_int, c_i64, c_ptr, c_i64, c_ptr]),
+    'o4d_layernorm_relu_f32': (c_int, [c_ptr, c_i64, c_int, c_ptr, c_ptr, ctypes.c_float, c_ptr, c_ptr]),
+    'o4d_layernorm_relu_backward_f32': (c_int, [c_ptr, c_ptr, c_i64, c_int, c_ptr, c_ptr, ctypes.c_float,
+                                                c_ptr, c_ptr, c_ptr, c_ptr]),
+    'o4d_col_mean_f32': (c_int, [c_ptr, c_i64, c_int, c_ptr, c_ptr]),
+    'o4d_col_mean_backward_f32': (c_int, [c_ptr, c_i64, c_int, c_ptr, c_ptr]),
 }
 
 _lib = None

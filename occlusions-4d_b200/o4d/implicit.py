@@ -11,7 +11,7 @@ from torch import nn
 
 from . import modules
 from . import ops
-from .point_transformer_layer import _no_grad_only
+from .point_transformer_layer import _wants_grad
 
 
 def positional_encode(points, base_frequency, num_powers):
@@ -60,9 +60,13 @@ class ResnetBlockFC(nn.Module):
         self.shortcut = None if d_in == d_out else nn.Linear(d_in, d_out, bias=False)
 
     def forward(self, x):
-        _no_grad_only(self, x)
         if isinstance(self.activation, Swish):
             self.activation(x)
+        if _wants_grad(self, x):
+            from . import autograd
+            net = autograd.linear(x, self.fc_0.weight, self.fc_0.bias, relu_in=True)
+            x_s = x if self.shortcut is None else autograd.linear(x, self.shortcut.weight)
+            return autograd.linear(net, self.fc_1.weight, self.fc_1.bias, residual=x_s, relu_in=True)
         net = ops.linear(x, self.fc_0.weight, self.fc_0.bias, relu_in=True)
         x_s = x if self.shortcut is None else ops.linear(x, self.shortcut.weight)
         return ops.linear(net, self.fc_1.weight, self.fc_1.bias, residual=x_s, relu_in=True)
@@ -101,9 +105,12 @@ class ResnetFC(nn.Module):
         """points (B,N,4), features (B,D) | (B,N,D) -> (output (B,N,G), penult (B,N,H)).
         Secondary mode of the reference (global-only / 'feature' conditioning): composed from
         o4d_linear_f32 calls, one per layer."""
-        _no_grad_only(self, points)
         if isinstance(self.activation, Swish):
             self.activation(points)
+        lin = ops.linear
+        if _wants_grad(self, points, features):
+            from . import autograd
+            lin = autograd.linear
         if len(points.shape) == 2:
             points = points.unsqueeze(0)
             features = features.unsqueeze(0)
@@ -120,16 +127,17 @@ class ResnetFC(nn.Module):
             raise NotImplementedError('o4d: d_in == 0 is not used by the reference callers')
         if self.pos_encoding_freqs > 0:
             points = positional_encode(points, 0.1, self.pos_encoding_freqs)
-        x = ops.linear(points, self.lin_in.weight, self.lin_in.bias)
+        x = lin(points, self.lin_in.weight, self.lin_in.bias)
         for blkid in range(self.n_blocks):
             if self.d_latent > 0:
-                z = ops.linear(features, self.lin_z[blkid].weight, self.lin_z[blkid].bias)
-                if len(z.shape) == 2:
-                    z = z.unsqueeze(1).expand_as(x)
-                x = x + z
+                if len(features.shape) == 2:
+                    z = lin(features, self.lin_z[blkid].weight, self.lin_z[blkid].bias)
+                    x = x + z.unsqueeze(1).expand_as(x)
+                else:   # per-point features: the add rides on the layer's residual input
+                    x = lin(features, self.lin_z[blkid].weight, self.lin_z[blkid].bias, residual=x)
             x = self.blocks[blkid](x)
         penult = x
-        output = ops.linear(x, self.lin_out.weight, self.lin_out.bias, relu_in=True)
+        output = lin(x, self.lin_out.weight, self.lin_out.bias, relu_in=True)
         if no_batch:
             output = output.squeeze(0)
             penult = penult.squeeze(0)
@@ -209,7 +217,6 @@ class LocalPclResnetFC(ResnetFC):
         features_abstract None; features_global (B,D) -> (output (B,N,G), penult (B,N,H)).
         B must be 1 (reference line 317).  pipeline.py:193-194 passes one more positional flag and
         unpacks one more value: a trailing None is returned in that case."""
-        _no_grad_only(self, points_query)
         if isinstance(self.activation, Swish):
             self.activation(points_query)
         if points_abstract is not None and features_abstract is None:
@@ -238,8 +245,14 @@ class LocalPclResnetFC(ResnetFC):
                 assert points_query.shape[-1] == self.d_in
                 assert features_global.shape[-1] + self.d_latent_local == self.d_latent
                 assert pcl_abstract.shape[-1] == 3 + self.d_latent_local
-                scene = self.o4d_scene(pcl_abstract[0], features_global[0])
-                out, pen = ops.decoder_forward(self.o4d_config(), self.o4d_params(), scene, points_query[0])
+                if _wants_grad(self, pcl_abstract, features_global):
+                    from . import autograd
+                    out, pen = autograd.decoder_train(self, ops._f32(points_query[0], 'points_query'),
+                                                      ops._f32(pcl_abstract[0], 'points_abstract'),
+                                                      ops._f32(features_global[0], 'features_global'))
+                else:
+                    scene = self.o4d_scene(pcl_abstract[0], features_global[0])
+                    out, pen = ops.decoder_forward(self.o4d_config(), self.o4d_params(), scene, points_query[0])
                 output, penult = out.unsqueeze(0), pen.unsqueeze(0)
             elif self.local_mode == 'feature':
                 raise NotImplementedError("o4d: local_mode 'feature' is not on the released path")

@@ -9,7 +9,7 @@ from torch import nn
 
 from . import modules
 from . import ops
-from .point_transformer_layer import _no_grad_only
+from .point_transformer_layer import _wants_grad
 
 
 class PointCompletionNetV3(nn.Module):
@@ -107,11 +107,11 @@ class PointCompletionNetV3(nn.Module):
         published model.py:148 defines; when that flag is present a trailing None is returned
         so both callers run unmodified."""
         assert pcl.dim() == 3 and pcl.shape[-1] == self.d_in
-        _no_grad_only(self, pcl)
         cfg = self.o4d_config()
         params = self.o4d_params()
         B, N, _ = pcl.shape
         outs, globs, coords = [], [], []
+        train_path = _wants_grad(self, pcl)
         for b in range(B):
             starts = None
             if self.fps_random_start:
@@ -119,7 +119,11 @@ class PointCompletionNetV3(nn.Module):
                 for _ in range(self.down_blocks):
                     starts.append(int(torch.randint(0, nl, (1,))))
                     nl = -(-nl // self.transition_factor)
-            res = ops.encoder_forward(cfg, params, pcl[b], starts, return_levels=bool(return_intermediate))
+            if train_path:
+                from . import autograd
+                res = autograd.encoder_train(self, ops._f32(pcl[b], 'pcl').contiguous(), starts)
+            else:
+                res = ops.encoder_forward(cfg, params, pcl[b], starts, return_levels=bool(return_intermediate))
             outs.append(res[0])
             globs.append(res[1])
             if return_intermediate:

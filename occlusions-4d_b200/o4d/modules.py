@@ -9,7 +9,7 @@ from torch import nn
 
 from . import ops
 from . import point_transformer_layer
-from .point_transformer_layer import _no_grad_only
+from .point_transformer_layer import _wants_grad
 
 
 class PointTransformerBlock(nn.Module):
@@ -41,7 +41,11 @@ class PointTransformerBlock(nn.Module):
         if not (self.d_in == self.d_hidden == self.d_out):
             raise NotImplementedError('o4d: PointTransformerBlock needs d_in == d_hidden == d_out '
                                       '(true for every block the reference builds)')
-        _no_grad_only(self, x)
+        if _wants_grad(self, x, x2):
+            from . import autograd
+            z = [autograd.pt_block_train(self, x[b], p[b], None if x2 is None else x2[b],
+                                         None if p2 is None else p2[b]) for b in range(x.shape[0])]
+            return (torch.stack(z), p)
         params = self.o4d_params()
         z = []
         for b in range(x.shape[0]):
@@ -86,11 +90,17 @@ class DownTransition(nn.Module):
         assert x.shape[:2] == p.shape[:2]
         if self.norm_type == 'batch':
             raise NotImplementedError("o4d: norm_type 'batch' is unused by the released configurations")
-        _no_grad_only(self, x)
         (B, N, _) = x.shape
         assert int(math.ceil(N / self.factor)) >= 1
         norm = 1 if self.norm_type == 'layer' else 0
         zs, ps = [], []
+        if _wants_grad(self, x):
+            from . import autograd
+            for b in range(B):
+                z, p_sub = autograd.down_train(self, x[b], p[b].contiguous(), self.o4d_start(N))
+                zs.append(z)
+                ps.append(p_sub)
+            return (torch.stack(zs), torch.stack(ps))
         for b in range(B):
             z, p_sub = ops.down_forward(self.o4d_params(), x[b], p[b], self.d_out, self.factor, self.knn_k,
                                         norm, self.o4d_start(N), self.o4d_precision)

@@ -51,3 +51,40 @@ def decode_sharded(decode_fn, query_all, batch_size, group=None):
     if world == 1:
         return local
     return all_gather_rows(local, query_all.shape[0], group)
+
+
+def allreduce_gradients(modules, group=None, bucket_bytes=32 << 20):
+    """Data-parallel gradient averaging, one sample per GPU (replaces nn.DataParallel at
+    train.py:305: the reference's loss is the mean over replicas of per-replica means,
+    pipeline.py:149-153 / loss.py:272-275, so gradients are AVERAGED over ranks).
+    Gradients are packed into flat buckets of about `bucket_bytes` (7.26 M fp32 parameters =
+    one 29 MB bucket for the released models), each reduced with one all_reduce(SUM) over
+    NCCL / NVLink and scaled by 1/world.  Parameters without a gradient on this rank
+    contribute zeros (every rank must walk the same parameter list).  Returns bucket count."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return 0
+    world = dist.get_world_size(group)
+    params = [p for m in modules for p in m.parameters() if p.requires_grad]
+    buckets, cur, cur_bytes = [], [], 0
+    for p in params:
+        nbytes = p.numel() * p.element_size()
+        if cur and cur_bytes + nbytes > bucket_bytes:
+            buckets.append(cur)
+            cur, cur_bytes = [], 0
+        cur.append(p)
+        cur_bytes += nbytes
+    if cur:
+        buckets.append(cur)
+    for bucket in buckets:
+        flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in bucket])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.div_(world)
+        off = 0
+        for p in bucket:
+            n = p.numel()
+            if p.grad is None:
+                p.grad = flat[off:off + n].reshape(p.shape).clone()
+            else:
+                p.grad.copy_(flat[off:off + n].reshape(p.shape))
+            off += n
+    return len(buckets)

@@ -10,13 +10,15 @@ from torch import nn
 from . import ops
 
 
-def _no_grad_only(module, *tensors):
-    """The CUDA path is forward-only for now: fail loudly instead of silently cutting the graph."""
-    if torch.is_grad_enabled() and module.training and any(
-            p.requires_grad for p in module.parameters()):
-        raise NotImplementedError(
-            'o4d: backward kernels are not built yet (see DESIGN.md "out of scope this round"); '
-            'call under torch.no_grad() or put the module in eval() mode')
+def _wants_grad(module, *tensors):
+    """True when the call must be differentiable: grad mode is on and a parameter or an input
+    requires grad.  Such calls go through o4d.autograd (forward + backward kernels with saved
+    activations); everything else takes the fused inference kernels."""
+    if not torch.is_grad_enabled():
+        return False
+    if any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors):
+        return True
+    return any(p.requires_grad for p in module.parameters())
 
 
 def square_distance(src, dst):
@@ -86,7 +88,11 @@ class PointTransformerLayer(nn.Module):
 
     def forward(self, x, pos, x2=None, pos2=None):
         """x (B,N,D), pos (B,N,3) [x2 (B,M,D2), pos2 (B,M,3)] -> (B,N,D)."""
-        _no_grad_only(self, x)
+        if _wants_grad(self, x, x2):
+            from . import autograd
+            return torch.stack([autograd.pt_layer_train(
+                self, x[b], pos[b], None if x2 is None else x2[b], None if pos2 is None else pos2[b])
+                for b in range(x.shape[0])])
         params = self.o4d_params()
         out = []
         for b in range(x.shape[0]):

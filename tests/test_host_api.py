@@ -33,7 +33,7 @@ def test_library_exports_every_header_symbol():
 
 def test_library_probes():
     L = _lib.lib()
-    assert L.o4d_abi_version() == 1
+    assert L.o4d_abi_version() == 2
     assert L.o4d_has_tcgen05() in (0, 1)
     assert L.o4d_last_error() is not None
 
@@ -137,11 +137,16 @@ def test_cpu_inputs_fail_loudly():
             o4d.kNN_torch(torch.zeros(1, 8, 3), torch.zeros(1, 8, 3), 2)
 
 
-def test_training_mode_with_grad_is_refused():
-    enc, _ = configs.build_modules(configs.TINY_GREATER)
+def test_training_path_has_no_cpu_fallback_either():
+    """With grad enabled the modules take the autograd path (o4d/autograd.py); CPU tensors must
+    still raise instead of silently differentiating through torch ops."""
+    enc, dec = configs.build_modules(configs.TINY_GREATER)
     enc.train()
-    with pytest.raises(NotImplementedError, match='backward'):
+    dec.train()
+    with pytest.raises(RuntimeError, match='CUDA only|move the module to CUDA'):
         enc(torch.zeros(1, 64, 8), False)
+    with pytest.raises(RuntimeError, match='CUDA only|move the module to CUDA'):
+        dec(torch.zeros(5, 4), torch.zeros(30, 3 + 64), torch.zeros(16), None)
 
 
 def test_missing_library_fails_loudly(monkeypatch):

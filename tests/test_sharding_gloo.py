@@ -34,6 +34,22 @@ def _worker(rank, world, port, ret):
     # ragged + empty shards
     tiny = parallel.decode_sharded(decode, q[:1], batch_size=128)
     ok = ok and torch.equal(tiny, decode(q[:1]))
+    # data-parallel gradient averaging (training, config 5): every rank ends with the mean over
+    # ranks, parameters without a local gradient count as zeros, buckets cover every parameter
+    torch.manual_seed(5)
+    net = torch.nn.Sequential(torch.nn.Linear(7, 9), torch.nn.Linear(9, 3), torch.nn.Linear(3, 2))
+    local = []
+    for i, p in enumerate(net.parameters()):
+        if i == 3 and rank == 1:
+            local.append(None)
+            continue
+        p.grad = torch.full_like(p, float(rank + 1)) * (i + 1)
+        local.append(p.grad.clone())
+    nb = parallel.allreduce_gradients([net], bucket_bytes=256)
+    ok = ok and nb >= 2
+    for i, p in enumerate(net.parameters()):
+        want = (1 + 2) * (i + 1) / 2.0 if i != 3 else 1 * (i + 1) / 2.0
+        ok = ok and bool(torch.allclose(p.grad, torch.full_like(p, want)))
     ret[rank] = bool(ok)
     dist.barrier()
     dist.destroy_process_group()

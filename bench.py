@@ -162,6 +162,74 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def train_step_bench(dev, world, rank, steps):
+    """BASELINE.json configs[4] per GPU: one CARLA-4D sample (14336 points), 4 frames x 17,203 query
+    points (args.py:254,257 / train.py:270-274), forward + backward through the nn.Module API
+    (o4d/autograd.py -> backward kernels), gradient averaging over ranks, AdamW.  The loss heads and the
+    optimizer are the caller's torch code (out of scope); the query sampler is
+    excluded.  Returns a dict for the bench line."""
+    import torch.distributed as dist
+    from o4d import parallel
+    from tests import configs
+    cfg = configs.C3_CARLA
+    enc, dec = configs.build_modules(cfg, dev)
+    enc.train()
+    dec.train()
+    params = list(enc.parameters()) + list(dec.parameters())
+    opt = torch.optim.AdamW(params, lr=1e-4)
+    g = torch.Generator().manual_seed(1830 + rank)
+    pcl = configs.synthetic_cloud(cfg).to(dev)
+    frames, per_frame = 4, 17203
+    lo = torch.tensor([0.0, -16.0, -1.0])
+    hi = torch.tensor([40.0, 16.0, 6.4])
+    queries = []
+    for f in range(frames):
+        q = torch.rand(per_frame, 4, generator=g)
+        q[:, :3] = q[:, :3] * (hi - lo) + lo
+        q[:, 3] = float(f)
+        queries.append(q.to(dev))
+    target = torch.rand(frames, per_frame, 6, generator=g).to(dev)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        abstract, glob, _ = enc(pcl[None], False)
+        total = 0.0
+        for f in range(frames):
+            out, _ = dec(queries[f], abstract[0], glob[0], None)
+            t = target[f]
+            loss = torch.nn.functional.binary_cross_entropy_with_logits(out[:, 0], (t[:, 0] > 0.5).float()) + \
+                (out[:, 1:4] - t[:, 1:4]).abs().mean() + \
+                torch.nn.functional.cross_entropy(out[:, 5:18], (t[:, 5] * 12.99).long())
+            total = total + loss
+        (total / frames).backward()
+        if world > 1:
+            parallel.allreduce_gradients([enc, dec])
+        opt.step()
+        return total
+
+    step()                                   # warm-up (workspaces, allocator)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        total = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    del opt
+    return {'ms_per_step': ms, 'samples_per_step': world, 'queries_per_sample': frames * per_frame,
+            'points_per_sample': cfg['n_points'], 'query_grads_per_s': world * frames * per_frame / (ms / 1e3),
+            'loss': float(total.detach()) / frames, 'steps': steps, 'precision': 'bf16x3 (fp32-grade) forward and backward',
+            'what': 'CARLA config 5 shape: encoder + 4 decoder frames forward/backward, grad all-reduce, AdamW; '
+                    'sampler excluded'}
+
+
 def run_o4d(args):
     import torch.distributed as dist
     import o4d
@@ -292,6 +360,11 @@ def run_o4d(args):
                         'measured': 'CUDA events around every launch of the family, one extra step after the timed region',
                         'whole_step_algorithmic_tflops': FLOP_PER_QUERY * value / world / 1e12}
 
+    train = None
+    if not args.no_train_step:
+        torch.cuda.empty_cache()
+        train = train_step_bench(dev, world, rank, max(1, min(args.steps, 3)))
+
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rate, secs, threads = cpu_reference_rate(args.cpu_sample)
@@ -309,7 +382,7 @@ def run_o4d(args):
                 'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'kernel_families': families,
                 'cpu_baseline': cpu_base,
                 'encoder': {'pts_per_s': cfg['n_points'] / (enc_ms / 1e3), 'ms': enc_ms, 'n_points': cfg['n_points']},
-                'tcgen05': bool(lib.o4d_has_tcgen05())}
+                'train_step': train, 'tcgen05': bool(lib.o4d_has_tcgen05())}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -325,6 +398,7 @@ def main():
     ap.add_argument('--precision', type=int, default=None, help='0 fp32 CUDA cores, 1 tcgen05 bf16x3, 2 bf16')
     ap.add_argument('--cpu-sample', type=int, default=196608)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-train-step', action='store_true', help='skip the config-5 training-step timing')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

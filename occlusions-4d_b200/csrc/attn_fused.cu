@@ -42,10 +42,22 @@ constexpr int OFF_WC = OFF_A2 + NBUF * 2 * R_BYTES;
 constexpr int OFF_W = OFF_WC + WC_STAGES * 2 * WC_BYTES;   // two stages of W_a2 chunks
 constexpr int ACC1_COL = 416;                // TMEM: [0, d) logits, [416, 512) three acc1 buffers
 constexpr int STG_LD = 33;                   // padded row pitch (floats) of the epilogue staging tiles
+// Gather staging: per hidden chunk the 32-float slices of Ka (one per tile row) and Qa (one per
+// query of the tile) are copied into shared memory with cp.async by lanes that cooperate on a row
+// (8 lanes x 16 B = one 128-byte line per row, 4 rows per warp instruction).  A row-per-thread
+// gather straight from global costs one L1 wavefront per lane per 16 bytes; ncu showed the LSU
+// data pipe at 74 % with the tensor pipe at 40 % (profiles/r1_i_*).  Row pitch 144 B: the
+// row-per-thread LDS.128 reads that follow are bank-conflict free.
+constexpr int G_PITCH = 144;
+constexpr int G_ROWS = BM + 16;              // 128 Ka rows + up to 16 Qa rows (k >= 8)
+constexpr int G_STAGE = G_ROWS * G_PITCH;    // 20,736 B
+constexpr int G_STAGES = 2;
+constexpr int TAIL_BYTES = 256 + BM * 4;     // mbarriers + TMEM slot, then the tile's neighbour ids
 
 __host__ __device__ inline int w2_bytes(int d) { return 2 * d * 32 * 2; }             // W_a2 chunk, hi + lo
 __host__ __device__ inline int wstage_bytes(int d) { return 2 * WC_BYTES + w2_bytes(d); }  // packed chunk in HBM
-__host__ __device__ inline int smem_bytes(int d) { return OFF_W + 2 * w2_bytes(d) + 256; }
+__host__ __device__ inline int off_g(int d) { return OFF_W + 2 * w2_bytes(d); }
+__host__ __device__ inline int smem_bytes(int d) { return off_g(d) + G_STAGES * G_STAGE + TAIL_BYTES; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t a, uint32_t count) {
@@ -115,6 +127,10 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
+// arrive on `mbar` (without raising its pending count) once every cp.async this thread issued so far has landed
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t mbar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(mbar) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 // 2^x for x <= 0 (softmax weights): single MUFU, flush-to-zero below 2^-126
@@ -161,6 +177,36 @@ __device__ __forceinline__ void store_a_half_row(uint8_t* hi_img, uint8_t* lo_im
 
 __device__ long long g_dbg[16];   // cycle stamps of one tile (diagnostics, read by o4d_debug_read)
 
+constexpr int EPI_WARPS = ROW_WARPS + 1;     // the weight-stream warp helps with the softmax reduce
+constexpr int EPI_GROUP = 2;                 // chunks staged per barrier pair
+
+// Per-channel softmax over a query's k staged rows and the weighted sum of (V + delta):
+// lane = channel inside the 32-channel chunk.  tile_l / tile_v: staging tiles [row][STG_LD].
+template <int KT>
+__device__ __forceinline__ void reduce_task(const float* tile_l, const float* tile_v, int q, int k, int lane,
+                                            float* out_row, const float* bias) {
+    constexpr int KV = KT ? KT : O4D_MAX_K;
+    const float* lq = tile_l + (q * k) * STG_LD + lane;
+    const float* vq = tile_v + (q * k) * STG_LD + lane;
+    float lgt[KV];
+    float mx = -3.4e38f;
+#pragma unroll
+    for (int jj = 0; jj < KV; ++jj)
+        if (jj < k) {
+            lgt[jj] = lq[jj * STG_LD];
+            mx = fmaxf(mx, lgt[jj]);
+        }
+    float den = 0.f, num = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < KV; ++jj)
+        if (jj < k) {
+            const float w = ex2_approx(lgt[jj] - mx);
+            den += w;
+            num = fmaf(w, vq[jj * STG_LD], num);
+        }
+    out_row[lane] = __fdividef(num, den) + bias[lane];
+}
+
 struct Params {
     const float* pos; int64_t ldpos;       // query coordinates (n, ldpos)
     const float* pos2; int64_t ldpos2;     // key coordinates (m, ldpos2)
@@ -189,15 +235,18 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fused_kernel(const Params p) 
     const int ND = d / 32;                  // output-column chunks of the softmax epilogue
     const int ntile = d > 256 ? 2 : 1;      // MMA2 is issued per n-tile of dn <= 256 columns
     const int dn = d / ntile;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_W + 2 * w2);
+    const int OFF_G = off_g(d);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_G + G_STAGES * G_STAGE);
     enum { W_FULL = 0, W_EMPTY = 2, WC_FULL = 4, WC_EMPTY = 8, ACC1_FULL = 12, A2_FULL = 15, A2_EMPTY = 18,
-           R_READY = 21, ACC2_FULL = 22, NBARS = 23 };
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+           R_READY = 21, ACC2_FULL = 22, G_FULL = 23, G_EMPTY = 25, NBARS = 27 };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
+    int32_t* s_j = reinterpret_cast<int32_t*>(smem + OFF_G + G_STAGES * G_STAGE + 256);   // neighbour id per tile row
     const uint32_t bar0 = smem_u32(bars);
 #define BAR(i) (bar0 + 8u * (uint32_t)(i))
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = smem_u32(smem);
 
+    if (threadIdx.x == 0 && blockIdx.x == gridDim.x / 2) { g_dbg[4] = clock64(); g_dbg[9] = 0; }
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) { mbar_init(BAR(W_FULL + i), 1); mbar_init(BAR(W_EMPTY + i), 1); }
         for (int i = 0; i < WC_STAGES; ++i) { mbar_init(BAR(WC_FULL + i), 1); mbar_init(BAR(WC_EMPTY + i), 1); }
@@ -208,6 +257,10 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fused_kernel(const Params p) 
         }
         mbar_init(BAR(R_READY), ROW_WARPS);
         mbar_init(BAR(ACC2_FULL), 1);
+        for (int i = 0; i < G_STAGES; ++i) {
+            mbar_init(BAR(G_FULL + i), ROW_WARPS * 32);   // one cp.async-completion arrival per row thread
+            mbar_init(BAR(G_EMPTY + i), ROW_WARPS);       // one arrival per row warp after its reads
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == ROW_WARPS) {
@@ -220,6 +273,12 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fused_kernel(const Params p) 
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // epilogue staging tiles (see the row warps' epilogue): 3 over the hidden buffers / Wc ring, 1 over W stage 1
+    constexpr int TILE_B = BM * STG_LD * 4;
+    auto tile_ptr = [&](int t) -> float* {
+        return reinterpret_cast<float*>(t < 3 ? smem + OFF_A2 + t * TILE_B : smem + OFF_W + w2);
+    };
+
     if (warp < ROW_WARPS) {
         // ================================================================== row warps
         // Two warps per TMEM lane quarter: thread (r, half) owns tile row r and columns
@@ -231,6 +290,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fused_kernel(const Params p) 
         const int64_t i = q0 + qi;
         const bool valid = (qi < p.tq) && (i < p.n);
         const int j = valid ? p.nbr[i * k + jn] : 0;
+        if (half == 0) s_j[r] = j;
         {
             float rv[16];
             if (valid) {
@@ -252,40 +312,60 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fused_kernel(const Params p) 
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(R_READY));
         }
-        const float* qrow = p.qa + (valid ? i : 0) * 2 * d + half * 16;
-        const float* krow = p.ka + (int64_t)j * 2 * d + half * 16;
         const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-        // Qa_i - Ka_j slice of the current chunk; the next chunk's slices are requested one
-        // iteration ahead and folded into `qk` at the end of the iteration (rows of padding
-        // queries compute finite garbage that nothing reads).
-        float qk[16];
-        float4 qn[4], kn[4];
+        // ---- gather staging (see G_PITCH): this warp copies 16 Ka rows and up to 2 Qa rows per chunk
+        asm volatile("bar.sync 1, 256;" ::: "memory");                 // s_j complete
+        const int g_piece = lane & 7, g_sub = lane >> 3;
+        const int g_rbase = (warp & 3) * 32 + (warp >> 2) * 16;
+        int gj[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            qn[e] = *reinterpret_cast<const float4*>(qrow + 4 * e);
-            kn[e] = *reinterpret_cast<const float4*>(krow + 4 * e);
-        }
+        for (int it = 0; it < 4; ++it) gj[it] = s_j[g_rbase + it * 4 + g_sub];
+        const int g_qi = warp * 2 + g_sub;                              // Qa row handled by lanes 0-15
+        const bool g_has_q = lane < 16 && g_qi < p.tq;
+        const int64_t g_qrow = min(q0 + (int64_t)g_qi, p.n - 1);
+        auto issue_gather = [&](int cn) {
+            const uint32_t gst = smem_base + OFF_G + (cn & 1) * G_STAGE;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            qk[4 * e] = qn[e].x - kn[e].x; qk[4 * e + 1] = qn[e].y - kn[e].y;
-            qk[4 * e + 2] = qn[e].z - kn[e].z; qk[4 * e + 3] = qn[e].w - kn[e].w;
-        }
+            for (int it = 0; it < 4; ++it)
+                cp_async16(gst + (g_rbase + it * 4 + g_sub) * G_PITCH + g_piece * 16,
+                           p.ka + (int64_t)gj[it] * 2 * d + cn * HC + g_piece * 4);
+            if (g_has_q)
+                cp_async16(gst + (BM + g_qi) * G_PITCH + g_piece * 16, p.qa + g_qrow * 2 * d + cn * HC + g_piece * 4);
+            cp_async_mbar_arrive_noinc(BAR(G_FULL + (cn & 1)));
+        };
+        issue_gather(0);
+        const int qi_rd = min(qi, p.tq - 1);                            // padding rows read a real query's slice
+        const uint32_t rd_k = OFF_G + r * G_PITCH + half * 64;
+        const uint32_t rd_q = OFF_G + (BM + qi_rd) * G_PITCH + half * 64;
         const bool dbg = (blockIdx.x == gridDim.x / 2) && threadIdx.x == 0;
         if (dbg) g_dbg[0] = clock64();
         for (int c = 0; c < NC; ++c) {
             const int b = c % NBUF;
             const uint32_t use = (uint32_t)(c / NBUF);
             if (c + 1 < NC) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    qn[e] = *reinterpret_cast<const float4*>(qrow + (c + 1) * HC + 4 * e);
-                    kn[e] = *reinterpret_cast<const float4*>(krow + (c + 1) * HC + 4 * e);
-                }
+                // stage (c+1)&1 was last read for chunk c-1: every row warp must have released it
+                const uint32_t gu = (uint32_t)((c + 1) >> 1);
+                if (gu > 0) mbar_wait(BAR(G_EMPTY + ((c + 1) & 1)), (gu - 1u) & 1u);
+                issue_gather(c + 1);
             }
             mbar_wait(BAR(ACC1_FULL + b), use & 1u);
             tc_fence_after();
             uint32_t acc[16];
             tmem_ld16_nowait(taddr + ACC1_COL + b * 32 + half * 16, acc);
+            mbar_wait(BAR(G_FULL + (c & 1)), (uint32_t)(c >> 1) & 1u);
+            float qk[16];
+            {
+                const uint8_t* gs = smem + (c & 1) * G_STAGE;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float4 qv = *reinterpret_cast<const float4*>(gs + rd_q + 16 * e);
+                    const float4 kv = *reinterpret_cast<const float4*>(gs + rd_k + 16 * e);
+                    qk[4 * e] = qv.x - kv.x; qk[4 * e + 1] = qv.y - kv.y;
+                    qk[4 * e + 2] = qv.z - kv.z; qk[4 * e + 3] = qv.w - kv.w;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(G_EMPTY + (c & 1)));        // this warp's reads of the stage are done
             tmem_ld_wait();
             float h[16];
 #pragma unroll
@@ -297,102 +377,102 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fused_kernel(const Params p) 
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(A2_FULL + b));
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                qk[4 * e] = qn[e].x - kn[e].x; qk[4 * e + 1] = qn[e].y - kn[e].y;
-                qk[4 * e + 2] = qn[e].z - kn[e].z; qk[4 * e + 3] = qn[e].w - kn[e].w;
-            }
         }
         // ------------------------------------------------ softmax / aggregation epilogue
         if (dbg) g_dbg[1] = clock64();
         mbar_wait(BAR(ACC2_FULL), 0);
         tc_fence_after();
         if (dbg) g_dbg[2] = clock64();
-        // Staging tiles [row][33] (padding: conflict-free row-wise stores and column-wise loads with
-        // immediate offsets only): buffer 0 over the idle hidden buffers / Wc ring, buffer 1 over the
-        // idle W stage 1 (W_p2 sits in stage 0).
-        const float* vrow = p.vtab + (int64_t)j * d + half * 16;
-        const float* brow = p.bp2 + half * 16;
-        float4 vv[4], bb[4];
+        // Staging tiles [row][33] of one 32-channel chunk (padding: conflict-free row-wise stores and
+        // column-wise loads): logits * scale and V + delta, 16.5 KB each.  The per-channel softmax over a
+        // query's k rows is a reduction ACROSS TMEM lanes, so it goes through shared memory.  Chunks are
+        // processed in groups of two (4 tiles: 3 over the idle hidden buffers / Wc ring, 1 over the idle W
+        // stage 1; W_p2 sits in W stage 0): 18 (chunk, query) tasks dealt round-robin to the 8 warps.
+        // The V_j slices of a group are fetched one group ahead into the two (now idle) gather stages by
+        // the same cooperative cp.async pattern as Ka in the main loop: a row-per-thread gather from global
+        // costs one L1 wavefront per lane (~1000 LSU cycles per chunk), and adding V in the reduce phase
+        // instead costs ~9 address instructions per load (measured: no gain).  b_p2 is added once per
+        // output instead of once per pair: a channel's softmax weights sum to one.
+        constexpr int GROUP = EPI_GROUP;
+        auto issue_v = [&](int cc, int slot) {
+            const uint32_t gst = smem_base + OFF_G + slot * G_STAGE;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            vv[e] = *reinterpret_cast<const float4*>(vrow + 4 * e);
-            bb[e] = *reinterpret_cast<const float4*>(brow + 4 * e);
-        }
-        for (int cc = 0; cc < ND; ++cc) {
-            const int g = NC + cc;
-            const int b = g % NBUF;
-            const uint32_t use = (uint32_t)(g / NBUF);
-            float* stg_l = reinterpret_cast<float*>((cc & 1) ? smem + OFF_W + w2 : smem + OFF_A2);
-            float* stg_v = stg_l + BM * STG_LD;
-            mbar_wait(BAR(ACC1_FULL + b), use & 1u);
-            tc_fence_after();
-            uint32_t dl[16], lg[16];
-            tmem_ld16_nowait(taddr + ACC1_COL + b * 32 + half * 16, dl);
-            tmem_ld16_nowait(taddr + cc * 32 + half * 16, lg);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(BAR(A2_FULL + b));      // acc1[b] drained
-            float* sl = stg_l + r * STG_LD + half * 16;
-            float* sv = stg_v + r * STG_LD + half * 16;
+            for (int it = 0; it < 4; ++it)
+                cp_async16(gst + (g_rbase + it * 4 + g_sub) * G_PITCH + g_piece * 16,
+                           p.vtab + (int64_t)gj[it] * d + cc * 32 + g_piece * 4);
+        };
+        // every warp has consumed the last Ka/Qa stage (its G_EMPTY arrival precedes this barrier)
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        issue_v(0, 0);
+        if (ND > 1) issue_v(1, 1);
+        cp_async_commit();
+        long long t_wait = 0, t_stage = 0, t_bar = 0, t_red = 0, t0 = 0;
+        for (int g0 = 0; g0 < ND; g0 += GROUP) {
+            const int gn = min(GROUP, ND - g0);
+            if (dbg) t0 = clock64();
+            cp_async_wait_all();
+            asm volatile("bar.sync 2, 288;" ::: "memory");         // V slices landed; previous group's tiles are free
+            if (dbg) t_bar += clock64() - t0;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                sl[4 * e + 0] = __uint_as_float(lg[4 * e + 0]) * p.scale_log2;
-                sl[4 * e + 1] = __uint_as_float(lg[4 * e + 1]) * p.scale_log2;
-                sl[4 * e + 2] = __uint_as_float(lg[4 * e + 2]) * p.scale_log2;
-                sl[4 * e + 3] = __uint_as_float(lg[4 * e + 3]) * p.scale_log2;
-                sv[4 * e + 0] = __uint_as_float(dl[4 * e + 0]) + (vv[e].x + bb[e].x);
-                sv[4 * e + 1] = __uint_as_float(dl[4 * e + 1]) + (vv[e].y + bb[e].y);
-                sv[4 * e + 2] = __uint_as_float(dl[4 * e + 2]) + (vv[e].z + bb[e].z);
-                sv[4 * e + 3] = __uint_as_float(dl[4 * e + 3]) + (vv[e].w + bb[e].w);
-            }
-            if (cc + 1 < ND) {   // next chunk's V / bias slices: in flight during the barrier and the reduce
+            for (int u = 0; u < GROUP; ++u) {
+                if (u >= gn) break;
+                const int cc = g0 + u;
+                const int g = NC + cc;
+                const int b = g % NBUF;
+                const uint32_t use = (uint32_t)(g / NBUF);
+                if (dbg) t0 = clock64();
+                mbar_wait(BAR(ACC1_FULL + b), use & 1u);
+                tc_fence_after();
+                if (dbg) { const long long t1 = clock64(); t_wait += t1 - t0; t0 = t1; }
+                uint32_t dl[16], lg[16];
+                tmem_ld16_nowait(taddr + ACC1_COL + b * 32 + half * 16, dl);
+                tmem_ld16_nowait(taddr + cc * 32 + half * 16, lg);
+                float4 vv[4];
+                {
+                    const uint8_t* vs = smem + OFF_G + u * G_STAGE + r * G_PITCH + half * 64;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) vv[e] = *reinterpret_cast<const float4*>(vs + 16 * e);
+                }
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(A2_FULL + b));      // acc1[b] drained
+                float* sl = tile_ptr(2 * u) + r * STG_LD + half * 16;
+                float* sv = tile_ptr(2 * u + 1) + r * STG_LD + half * 16;
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    vv[e] = *reinterpret_cast<const float4*>(vrow + (cc + 1) * 32 + 4 * e);
-                    bb[e] = *reinterpret_cast<const float4*>(brow + (cc + 1) * 32 + 4 * e);
+                    sl[4 * e + 0] = __uint_as_float(lg[4 * e + 0]) * p.scale_log2;
+                    sl[4 * e + 1] = __uint_as_float(lg[4 * e + 1]) * p.scale_log2;
+                    sl[4 * e + 2] = __uint_as_float(lg[4 * e + 2]) * p.scale_log2;
+                    sl[4 * e + 3] = __uint_as_float(lg[4 * e + 3]) * p.scale_log2;
+                    sv[4 * e + 0] = __uint_as_float(dl[4 * e + 0]) + vv[e].x;
+                    sv[4 * e + 1] = __uint_as_float(dl[4 * e + 1]) + vv[e].y;
+                    sv[4 * e + 2] = __uint_as_float(dl[4 * e + 2]) + vv[e].z;
+                    sv[4 * e + 3] = __uint_as_float(dl[4 * e + 3]) + vv[e].w;
                 }
+                if (dbg) t_stage += clock64() - t0;
             }
-            // one barrier per chunk: staging buffers alternate, so the next chunk's stores cannot
-            // overtake this chunk's reduce (they are separated by the next barrier)
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            // lane = channel inside the chunk; the warp that takes two queries rotates with cc
-            for (int q = (warp + cc) & 7; q < p.tq; q += ROW_WARPS) {
+            if (dbg) t0 = clock64();
+            asm volatile("bar.sync 2, 288;" ::: "memory");         // the group's tiles are complete, V stages consumed
+            if (dbg) { const long long t1 = clock64(); t_bar += t1 - t0; t0 = t1; }
+            if (g0 + GROUP < ND) {                                  // next group's V slices: in flight during the reduce
+                issue_v(g0 + GROUP, 0);
+                if (g0 + GROUP + 1 < ND) issue_v(g0 + GROUP + 1, 1);
+                cp_async_commit();
+            }
+            if (dbg) { const long long t1 = clock64(); g_dbg[9] += t1 - t0; t0 = t1; }
+            // task = (chunk u, query q), dealt round-robin to the 8 row warps and the weight-stream warp
+            const int ntask = gn * p.tq;
+            for (int task = warp; task < ntask; task += EPI_WARPS) {
+                const int u = task >= p.tq ? 1 : 0, q = task - u * p.tq;
                 const int64_t gi = q0 + q;
-                if (gi < p.n) {
-                    const float* lq = stg_l + (q * k) * STG_LD + lane;
-                    const float* vq = stg_v + (q * k) * STG_LD + lane;
-                    float num, den;
-                    if (KT) {
-                        float lgt[KT ? KT : 1];
-                        float mx = -3.4e38f;
-#pragma unroll
-                        for (int jj = 0; jj < KT; ++jj) {
-                            lgt[jj] = lq[jj * STG_LD];
-                            mx = fmaxf(mx, lgt[jj]);
-                        }
-                        den = 0.f; num = 0.f;
-#pragma unroll
-                        for (int jj = 0; jj < KT; ++jj) {
-                            const float w = ex2_approx(lgt[jj] - mx);
-                            den += w;
-                            num = fmaf(w, vq[jj * STG_LD], num);
-                        }
-                    } else {
-                        float mx = -3.4e38f;
-                        for (int jj = 0; jj < k; ++jj) mx = fmaxf(mx, lq[jj * STG_LD]);
-                        den = 0.f; num = 0.f;
-                        for (int jj = 0; jj < k; ++jj) {
-                            const float w = ex2_approx(lq[jj * STG_LD] - mx);
-                            den += w;
-                            num = fmaf(w, vq[jj * STG_LD], num);
-                        }
-                    }
-                    p.out[gi * d + cc * 32 + lane] = __fdividef(num, den);
-                }
+                if (gi < p.n)
+                    reduce_task<KT>(tile_ptr(2 * u), tile_ptr(2 * u + 1), q, k, lane, p.out + gi * d + (g0 + u) * 32,
+                                    p.bp2 + (g0 + u) * 32);
             }
+            if (dbg) t_red += clock64() - t0;
         }
+        if (dbg) { g_dbg[5] = t_wait; g_dbg[6] = t_stage; g_dbg[7] = t_bar; g_dbg[8] = t_red; }
         if (dbg) g_dbg[3] = clock64();
         tc_fence_before();
     } else if (warp == ROW_WARPS) {
@@ -420,6 +500,22 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fused_kernel(const Params p) 
             mbar_wait(BAR(W_EMPTY + 0), (use & 1u) ^ 1u);
             mbar_arrive_expect_tx(BAR(W_FULL + 0), (uint32_t)(2 * d * 64));
             bulk_g2s(smem_base + OFF_W, p.wp2, (uint32_t)(2 * d * 64), BAR(W_FULL + 0));
+        }
+        __syncwarp();
+        // ---- epilogue helper: ninth reduce warp (same barrier sequence as the row warps' epilogue)
+        const int64_t q0 = (int64_t)blockIdx.x * p.tq;
+        for (int g0 = 0; g0 < ND; g0 += EPI_GROUP) {
+            const int gn = min(EPI_GROUP, ND - g0);
+            asm volatile("bar.sync 2, 288;" ::: "memory");
+            asm volatile("bar.sync 2, 288;" ::: "memory");         // the group's tiles are complete
+            const int ntask = gn * p.tq;
+            for (int task = ROW_WARPS; task < ntask; task += EPI_WARPS) {
+                const int u = task >= p.tq ? 1 : 0, q = task - u * p.tq;
+                const int64_t gi = q0 + q;
+                if (gi < p.n)
+                    reduce_task<KT>(tile_ptr(2 * u), tile_ptr(2 * u + 1), q, k, lane, p.out + gi * d + (g0 + u) * 32,
+                                    p.bp2 + (g0 + u) * 32);
+            }
         }
     } else {
         // ================================================================== MMA issuer

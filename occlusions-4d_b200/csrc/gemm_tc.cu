@@ -7,14 +7,17 @@
 // same fp32 TMEM accumulator ("bf16x3", precision 1).  precision 2 issues only hi*hi.
 //
 // Per CTA: one 128 x BN output tile (BN <= 256 TMEM columns), K walked in chunks of 32.
-//   warps 0-3  A producers: coalesced fp32 loads (optionally ReLU), hi/lo split, 16-byte
+//   warps 0-7  A producers: coalesced fp32 loads (optionally ReLU), hi/lo split, 16-byte
 //              stores into the K-major no-swizzle core-matrix layout the UMMA descriptor
 //              describes; after the main loop the same warps run the epilogue
-//              (tcgen05.ld 32x32b -> bias / ReLU / residual -> global).
-//   warp 4     allocates TMEM; lane 0 streams the pre-packed weight tiles (hi+lo image of a
+//              (tcgen05.ld 32x32b -> bias / ReLU / residual -> global): warp w owns TMEM lane
+//              quarter w & 3 and column half w >> 2.  (In-kernel cycle stamps showed the main loop
+//              producer-bound -- identical with one MMA pass instead of three -- and the epilogue as
+//              long as 60 % of it, so both run on eight warps instead of four.)
+//   warp 8     allocates TMEM; lane 0 streams the pre-packed weight tiles (hi+lo image of a
 //              BN x 32 slab, already in shared-memory layout) with cp.async.bulk (TMA engine,
 //              mbarrier complete_tx).
-//   warp 5     lane 0 issues tcgen05.mma and commits to the stage's "empty" mbarrier.
+//   warp 9     lane 0 issues tcgen05.mma and commits to the stage's "empty" mbarrier.
 // Two CTAs are resident per SM (2 x ~97 KB smem, 2 x 256 TMEM columns), so one CTA's
 // epilogue overlaps the other's main loop.
 #include "o4d_common.cuh"
@@ -26,7 +29,8 @@ namespace tc {
 constexpr int BM = 128;
 constexpr int BK = 32;
 constexpr int STAGES = 2;
-constexpr int THREADS = 192;
+constexpr int PROD_WARPS = 8;
+constexpr int THREADS = (PROD_WARPS + 2) * 32;
 constexpr int A_HALF_BYTES = BM * BK * 2;          // one bf16 image of the A slab (8 KB)
 constexpr int BN_MAX = 256;
 constexpr int STAGE_BYTES = 2 * A_HALF_BYTES + 2 * BN_MAX * BK * 2;  // 48 KB
@@ -180,13 +184,13 @@ linear_tc_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda, 
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(full0 + 8 * s, 5);   // 4 producer warps + the weight-copy thread
+            mbar_init(full0 + 8 * s, PROD_WARPS + 1);   // producer warps + the weight-copy thread
             mbar_init(empty0 + 8 * s, 1);  // one tcgen05.commit
         }
         mbar_init(accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
+    if (warp == PROD_WARPS) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -198,18 +202,19 @@ linear_tc_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda, 
     const int nchunks = m.kchunks;
     const uint32_t b_half_bytes = (uint32_t)bn * BK * 2;
 
-    if (warp < 4) {
+    if (warp < PROD_WARPS) {
         // ------------------------------------------------------------ A producers
         // The fp32 -> bf16 hi/lo conversion needs the data in registers, so the global loads of
         // chunk c+1 are issued BEFORE chunk c is converted and stored: their latency hides behind
         // the stage wait, the conversion and the shared-memory stores of the current chunk.
         const bool relu_in = flags & O4D_RELU_IN;
         const int kc = lane >> 3, rr = lane & 7;
-        auto load_chunk = [&](int c, float (&v)[4][8]) {
+        constexpr int GPW = (BM / 8) / PROD_WARPS;      // 8-row groups per producer warp (2)
+        auto load_chunk = [&](int c, float (&v)[GPW][8]) {
             const int gk = c * BK + kc * 8;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                const int64_t grow = row0 + (warp * 4 + g) * 8 + rr;
+            for (int g = 0; g < GPW; ++g) {
+                const int64_t grow = row0 + (warp * GPW + g) * 8 + rr;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[g][i] = 0.f;
                 if (grow < rows) {
@@ -227,7 +232,7 @@ linear_tc_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda, 
                 }
             }
         };
-        float cur[4][8], nxt[4][8];
+        float cur[GPW][8], nxt[GPW][8];
         const bool dbg = (blockIdx.x == gridDim.x / 2) && blockIdx.y == 0 && threadIdx.x == 0;
         if (dbg) g_dbg_tc[0] = clock64();
         load_chunk(0, cur);
@@ -239,8 +244,8 @@ linear_tc_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda, 
             uint8_t* a_hi = smem + s * STAGE_BYTES;
             uint8_t* a_lo = a_hi + A_HALF_BYTES;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                const int rg = warp * 4 + g;                  // 8-row group inside the 128-row tile
+            for (int g = 0; g < GPW; ++g) {
+                const int rg = warp * GPW + g;                // 8-row group inside the 128-row tile
                 __align__(16) __nv_bfloat16 h[8];
                 __align__(16) __nv_bfloat16 l[8];
 #pragma unroll
@@ -256,7 +261,7 @@ linear_tc_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda, 
             __syncwarp();
             if (lane == 0) mbar_arrive(full0 + 8 * s);
 #pragma unroll
-            for (int g = 0; g < 4; ++g)
+            for (int g = 0; g < GPW; ++g)
 #pragma unroll
                 for (int i = 0; i < 8; ++i) cur[g][i] = nxt[g][i];
         }
@@ -272,9 +277,14 @@ linear_tc_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda, 
         tc_fence_after();
         if (dbg) g_dbg_tc[2] = clock64();
         const bool relu_out = flags & O4D_RELU_OUT;
-        const int64_t warp_row0 = row0 + warp * 32;
+        const int quarter = warp & 3, chalf = warp >> 2;
+        const int64_t warp_row0 = row0 + quarter * 32;
         const int col_base = tile_n * bn;
-        const uint32_t taddr_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const uint32_t taddr_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        // column range of this warp: 32-column blocks [0, nblk/2 rounded up) or the rest
+        const int nblk = (bn + 31) / 32;
+        const int c_begin = chalf ? ((nblk + 1) / 2) * 32 : 0;
+        const int c_end = chalf ? bn : min(bn, ((nblk + 1) / 2) * 32);
         constexpr int SLD = 36;                            // staging row pitch (floats): 16-byte aligned rows, conflict-free
         float* stg = reinterpret_cast<float*>(smem) + warp * (32 * SLD);
         const int rows_here = (int)min((int64_t)32, rows - warp_row0);     // may be <= 0 for a ragged last tile
@@ -295,13 +305,13 @@ linear_tc_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda, 
                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             };
-            load_res(0);
-            for (int c0 = 0; c0 < bn; c0 += 32) {
+            if (c_begin < c_end) load_res(c_begin);
+            for (int c0 = c_begin; c0 < c_end; c0 += 32) {
                 const int width = min(32, bn - c0);
                 float4 res[8];
 #pragma unroll
                 for (int it = 0; it < 8; ++it) res[it] = resn[it];
-                if (c0 + 32 < bn) load_res(c0 + 32);
+                if (c0 + 32 < c_end) load_res(c0 + 32);
                 float v[32];
                 tmem_ld16(taddr_row + (uint32_t)c0, v);
                 if (width > 16) tmem_ld16(taddr_row + (uint32_t)(c0 + 16), v + 16);
@@ -336,7 +346,7 @@ linear_tc_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda, 
                 gq = g.qa + (ar / g.knbr) * m.n;
                 gk = g.ka + (int64_t)g.nbr[ar] * m.n;
             }
-            for (int c0 = 0; c0 < bn; c0 += 16) {
+            for (int c0 = c_begin; c0 < c_end; c0 += 16) {
                 float v[16];
                 tmem_ld16(taddr_row + (uint32_t)c0, v);
                 if (grow < rows) {
@@ -353,7 +363,7 @@ linear_tc_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda, 
         }
         if (dbg) g_dbg_tc[3] = clock64();
         tc_fence_before();
-    } else if (warp == 4) {
+    } else if (warp == PROD_WARPS) {
         // ------------------------------------------------------------ weight slabs via the TMA engine
         if (lane == 0) {
             const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(Wp) + (size_t)tile_n * nchunks * 2 * b_half_bytes;
@@ -398,7 +408,7 @@ linear_tc_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda, 
         }
     }
     __syncthreads();
-    if (warp == 4) {
+    if (warp == PROD_WARPS) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
     }

@@ -15,8 +15,8 @@ cat $OUT/bench_reference.json
 fi
 if [ "$SKIP_NCU" != "1" ]; then
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $OUT/launches.csv \
-    python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_launch_bench.log 2>&1; echo "ncu launches exit $?"
+    python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-train-step > $OUT/ncu_launch_bench.log 2>&1; echo "ncu launches exit $?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'attn_fused_kernel|linear_tc_kernel' -s 40 -c 4 \
-    -o $OUT/prof_top python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_full.log 2>&1; echo "ncu full exit $?"
+    -o $OUT/prof_top python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-train-step > $OUT/ncu_full.log 2>&1; echo "ncu full exit $?"
 ls -la $OUT
 fi

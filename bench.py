@@ -57,7 +57,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                          '--format=csv,noheader,nounits', '-lms', '50'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -353,8 +353,14 @@ def run_o4d(args):
                 peak, which = 1400.0, 'fallback (B200_PROFILING.md sustained ~1.4 PFLOP/s)'
             step_total = sum(f['ms'] for f in families.values())
             ach = families[top]['tflops']
+            traffic = None
+            tpath = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+            if os.path.isfile(tpath):      # dram bytes per launch of the dominant kernel, from the committed ncu capture
+                traffic = json.load(open(tpath)).get(top, {}).get('dram_bytes_per_launch')
             roofline = {'bound': 'tensor', 'kernel': top, 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s',
-                        'frac': ach / peak, 'traffic': None, 'peak_source': which,
+                        'frac': ach / peak, 'traffic': traffic,
+                        'traffic_source': 'profiles/ncu_traffic.json (ncu --set full, dram__bytes_read+write per launch)',
+                        'peak_source': which,
                         'share_of_step': families[top]['ms'] / step_total if step_total else None,
                         'avg_launch_ms': families[top]['ms'] / families[top]['launches'],
                         'measured': 'CUDA events around every launch of the family, one extra step after the timed region',

@@ -12,6 +12,7 @@
 // counting pass (indices may repeat when the cloud holds duplicates, e.g. zero padding).
 #include "o4d_common.cuh"
 #include <math_constants.h>
+#include <stdlib.h>
 
 namespace o4d {
 
@@ -244,6 +245,19 @@ fps_emit_sorted_kernel(const int32_t* __restrict__ counts, int n, int32_t* __res
     }
 }
 
+// 8-CTA cluster version (fps_cluster.cu); O4D_E_UNSUPPORTED when the cloud does not fit it.
+int fps_cluster_launch(const float* xyz, int64_t n, int64_t ld, int64_t n_out, int64_t start, int32_t* counts,
+                       int64_t* order64, cudaStream_t st);
+
+static bool fps_cluster_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("O4D_FPS_CLUSTER");      // 0 = single-SM kernel only (A/B timing)
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
 static size_t fps_ws_bytes(int64_t n) {
     return align_up((size_t)n * sizeof(int32_t), 256) + align_up((size_t)n * sizeof(float), 256);
 }
@@ -265,6 +279,15 @@ int fps_launch(const float* xyz, int64_t n, int64_t ld, int64_t n_out, int64_t s
     int32_t* counts = (int32_t*)ws;
     float* mind = (float*)((char*)ws + align_up((size_t)n * sizeof(int32_t), 256));
     O4D_CUDA(cudaMemsetAsync(counts, 0, (size_t)n * sizeof(int32_t), st));
+    if (fps_cluster_enabled()) {
+        const int rc = fps_cluster_launch(xyz, n, ld, n_out, start, counts, order64, st);
+        if (rc == 0) {
+            fps_emit_sorted_kernel<<<1, FPS_THREADS, 0, st>>>(counts, (int)n, sorted32, sorted64);
+            O4D_LAUNCH_CHECK();
+            return 0;
+        }
+        if (rc != O4D_E_UNSUPPORTED) return rc;
+    }
     const int ppt = (int)cdiv(n, FPS_THREADS);
 #define O4D_FPS_CASE(PV)                                                                        \
     fps_kernel<PV><<<1, FPS_THREADS, 0, st>>>(xyz, (int)n, ld, (int)n_out, (int)start, counts,  \

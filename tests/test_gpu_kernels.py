@@ -87,7 +87,10 @@ def test_knn_rejects_bad_arguments():
 # ------------------------------------------------------------------------------ FPS
 
 @pytest.mark.parametrize('n,n_out,start', [(76, 26, 0), (2048, 683, 0), (2048, 683, 77), (14336, 4779, 0),
-                                           (1593, 531, 5), (20000, 300, 3)])
+                                           (1593, 531, 5), (20000, 300, 3),
+                                           # 8-CTA cluster kernel (2048 < n <= 17066): 1, 2, 4 and 5 points per thread
+                                           (2049, 683, 0), (4779, 1593, 11), (8192, 700, 8191), (14336, 4779, 123),
+                                           (16384, 200, 1), (17000, 150, 9)])
 def test_fps_matches_oracle(n, n_out, start):
     g = torch.Generator().manual_seed(n)
     p = torch.rand(n, 3, generator=g) * 10 - 5
@@ -105,6 +108,19 @@ def test_fps_zero_padded_cloud_repeats_like_argmax():
     p[:5] = torch.rand(5, 3) + 1.0
     want = cluster_ops.fps_segment(p, 22, 0)
     got_sorted, got_order = ops.fps(p.to(DEV), 22, 0, return_order=True)
+    assert torch.equal(got_order.cpu(), want)
+    assert torch.equal(got_sorted.cpu(), torch.sort(want)[0])
+
+
+def test_fps_cluster_kernel_ties_and_single_sm_kernel_agree(monkeypatch):
+    """Zero-padded duplicates (geometry.py:320-322) at a size the cluster kernel takes: exact ties must
+    resolve to the lowest index, identically to the oracle."""
+    g = torch.Generator().manual_seed(2)
+    p = torch.rand(6000, 3, generator=g) * 8 - 4
+    p[5000:] = 0.0
+    p[100] = p[4000]
+    want = cluster_ops.fps_segment(p, 2000, 0)
+    got_sorted, got_order = ops.fps(p.to(DEV), 2000, 0, return_order=True)
     assert torch.equal(got_order.cpu(), want)
     assert torch.equal(got_sorted.cpu(), torch.sort(want)[0])
 

@@ -107,6 +107,7 @@ static void for_each_tc_weight(const o4d_decoder_config* c, const DecParams& d, 
     const int H = c->d_hidden, E = c->d_latent_local, Dg = c->d_latent - c->d_latent_local;
     const int pe_w = c->pos_encoding_freqs > 0 ? c->d_in * (2 * c->pos_encoding_freqs + 1) : c->d_in;
     fn(d.lin_in_w, H, pe_w, pe_w);
+    fn(d.lin_out_w, c->d_out, H, H);
     for (int b = 0; b < c->n_blocks; ++b) {
         fn(d.z_w[b] ? d.z_w[b] + Dg : nullptr, H, E, c->d_latent);  // local half of lin_z (column slice)
         fn(d.fc0_w[b], H, H, H);
@@ -278,8 +279,8 @@ int decoder_forward(const o4d_decoder_config* c, const float* const* P, const vo
     }
     if (penult) O4D_TRY(copy2d_launch(w.x, H, nq, H, penult, H, st));           // implicit.py:441
     // implicit.py:442-443
-    return linear_launch(w.x, nq, H, H, d.lin_out_w, d.lin_out_b, c->d_out, nullptr, 0, out, c->d_out, O4D_RELU_IN,
-                         prec, st);
+    return linear_ps_launch(&ps, w.x, nq, H, H, d.lin_out_w, H, d.lin_out_b, c->d_out, nullptr, 0, out, c->d_out,
+                            O4D_RELU_IN, prec, st);
 }
 
 }  // namespace o4d

@@ -1,40 +1,29 @@
-// tcgen05 dense layer:  C = post(pre(A) @ W^T + bias) [+ R]   with fp32 tensors in HBM.
+// 2-CTA (cta_group::2) version of the tcgen05 dense layer in gemm_tc.cu.
 //
-// The reference runs every nn.Linear as a cuBLAS fp32 SGEMM.  Here the contraction runs on
-// the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM) while keeping
-// fp32-grade results: both operands are split on the fly into bf16 hi + bf16 lo
-// (x = hi + lo + O(2^-17 |x|)) and three MMAs accumulate hi*hi + lo*hi + hi*lo into the
-// same fp32 TMEM accumulator ("bf16x3", precision 1).  precision 2 issues only hi*hi.
-//
-// Per CTA: one 128 x BN output tile (BN <= 256 TMEM columns), K walked in chunks of 32.
-//   warps 0-7  A producers: coalesced fp32 loads (optionally ReLU), hi/lo split, 16-byte
-//              stores into the K-major no-swizzle core-matrix layout the UMMA descriptor
-//              describes; after the main loop the same warps run the epilogue
-//              (tcgen05.ld 32x32b -> bias / ReLU / residual -> global): warp w owns TMEM lane
-//              quarter w & 3 and column half w >> 2.  (In-kernel cycle stamps showed the main loop
-//              producer-bound -- identical with one MMA pass instead of three -- and the epilogue as
-//              long as 60 % of it, so both run on eight warps instead of four.)
-//   warp 8     allocates TMEM; lane 0 streams the pre-packed weight tiles (hi+lo image of a
-//              BN x 32 slab, already in shared-memory layout) with cp.async.bulk (TMA engine,
-//              mbarrier complete_tx).
-//   warp 9     lane 0 issues tcgen05.mma and commits to the stage's "empty" mbarrier.
-// Two CTAs are resident per SM (2 x ~97 KB smem, 2 x 256 TMEM columns), so one CTA's
-// epilogue overlaps the other's main loop.
+// Measured in round 1: the dense layer is bound by bytes entering the SM
+// (~30 B/cycle/SM), of which 62 % are weights every CTA re-streams for its 128 rows.  Here two
+// CTAs of a cluster (two SMs of one TPC) form a pair: each loads its own 128 rows of A but only
+// HALF of the weight tile's rows; the leader CTA issues tcgen05.mma.cta_group::2 (M = 256:
+// rows 0-127 accumulate in the leader's TMEM, rows 128-255 in the peer's, B read half from each
+// CTA's shared memory), so weight ingest per SM halves (42.6 -> 29.3 KB per 32-wide K chunk).
+//   full[s]  (leader) : 8 local producer arrivals + 1 local weight copy + 8 remote producer arrivals;
+//                       the peer's warp 0 first waits for the peer's own weight half (peer-local full[s])
+//   empty[s], accum   : tcgen05.commit ... multicast::cluster -> the barrier at the same offset in both CTAs
+// Everything else (producers, epilogue, bf16x3 split) is the 1-CTA kernel's.
 #include "o4d_common.cuh"
 #include <cuda_bf16.h>
-#include <stdlib.h>
 
 namespace o4d {
-namespace tc {
+namespace tc2 {
 
 constexpr int BM = 128;
 constexpr int BK = 32;
-constexpr int STAGES = 2;
+constexpr int STAGES = 3;
 constexpr int PROD_WARPS = 8;
 constexpr int THREADS = (PROD_WARPS + 2) * 32;
 constexpr int A_HALF_BYTES = BM * BK * 2;          // one bf16 image of the A slab (8 KB)
 constexpr int BN_MAX = 256;
-constexpr int STAGE_BYTES = 2 * A_HALF_BYTES + 2 * BN_MAX * BK * 2;  // 48 KB
+constexpr int STAGE_BYTES = 2 * A_HALF_BYTES + 2 * (BN_MAX / 2) * BK * 2;  // 32 KB: own A rows + this CTA's half of the B rows
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -67,6 +56,39 @@ __device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) {
         if (clock64() - t0 > 4000000000LL) __trap();
     }
 }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t local_addr, uint32_t rank) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(rank));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cl(uint32_t a, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(a), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cl(uint32_t a, uint32_t parity) {
+    if (mbar_try_wait_cl(a, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait_cl(a, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -90,19 +112,22 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 
 // kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M = 128.
 __device__ __forceinline__ uint32_t umma_idesc(int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
 }
 
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// arrives on the mbarrier at this offset in BOTH CTAs of the pair once the MMAs issued so far have retired
 __device__ __forceinline__ void umma_commit(uint32_t mbar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(mbar),
+                 "h"((uint16_t)3)
+                 : "memory");
 }
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
@@ -122,7 +147,7 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
     lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
 
-__device__ long long g_dbg_tc[16];   // cycle stamps of one CTA (diagnostics)
+__device__ long long g_dbg_tc2[16];   // cycle stamps of one CTA (diagnostics)
 
 struct PackMeta {
     int n, k;      // logical weight shape
@@ -148,35 +173,41 @@ __host__ __device__ inline size_t pack_bytes(const PackMeta& m) {
     return (size_t)m.ntiles * m.kchunks * 2 * m.bn * BK * 2;
 }
 
-// W (n, k) fp32 row-major (ldw) -> per (n-tile, k-chunk): [hi image][lo image], each
-// [kc = 4][row-group = bn/8][8 rows][8 bf16] -- exactly the shared-memory image of the slab.
-__global__ void pack_weight_kernel(const float* __restrict__ W, int64_t ldw, PackMeta m, __nv_bfloat16* __restrict__ out) {
+// W (n, k) fp32 row-major (ldw) -> per (n-tile, k-chunk): [half 0 hi][half 0 lo][half 1 hi][half 1 lo],
+// half h = rows [h * bn/2, (h+1) * bn/2) of the tile, each image [kc = 4][row-group][8 rows][8 bf16]:
+// exactly what CTA h of the pair copies into its shared memory.
+__global__ void pack_weight_pair_kernel(const float* __restrict__ W, int64_t ldw, PackMeta m, __nv_bfloat16* __restrict__ out) {
     const int64_t slab_elems = (int64_t)m.bn * BK;
     const int64_t total = (int64_t)m.ntiles * m.kchunks * slab_elems;
+    const int hb = m.bn / 2;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
         const int64_t slab = e / slab_elems;
         const int within = (int)(e % slab_elems);
         const int t = (int)(slab / m.kchunks), c = (int)(slab % m.kchunks);
-        const int kc = within / (m.bn * 8);
-        const int rem = within % (m.bn * 8);
-        const int row = rem / 8, el = rem % 8;      // row = rg*8 + r8
-        const int gn = t * m.bn + row, gk = c * BK + kc * 8 + el;
+        const int half = within / (hb * BK);
+        const int w2 = within % (hb * BK);
+        const int kc = w2 / (hb * 8);
+        const int rem = w2 % (hb * 8);
+        const int row = rem / 8, el = rem % 8;
+        const int gn = t * m.bn + half * hb + row, gk = c * BK + kc * 8 + el;
         float v = (gn < m.n && gk < m.k) ? W[(int64_t)gn * ldw + gk] : 0.f;
         __nv_bfloat16 hi, lo;
         split_bf16(v, hi, lo);
-        out[slab * 2 * slab_elems + within] = hi;
-        out[slab * 2 * slab_elems + slab_elems + within] = lo;
+        __nv_bfloat16* dst = out + slab * 2 * slab_elems + (int64_t)half * 2 * hb * BK;
+        dst[w2] = hi;
+        dst[hb * BK + w2] = lo;
     }
 }
 
 __global__ void __launch_bounds__(THREADS, 2)
-linear_tc_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda, const __nv_bfloat16* __restrict__ Wp,
+linear_tc2_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda, const __nv_bfloat16* __restrict__ Wp,
                  PackMeta m, const float* __restrict__ bias, const float* R, int64_t ldr, float* C, int64_t ldc,
                  int flags, int split, RowGather g) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);  // full[2], empty[2], accum
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();          // 0 = leader (issues the MMAs of the pair), 1 = peer
     const int64_t row0 = (int64_t)blockIdx.x * BM;
     const int tile_n = blockIdx.y;
     const int bn = m.bn;
@@ -185,23 +216,27 @@ linear_tc_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda, 
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(full0 + 8 * s, PROD_WARPS + 1);   // producer warps + the weight-copy thread
+            // leader: its producer warps + its weight copy + the peer's producer warps (whose warp 0 also
+            // vouches for the peer's weight half); peer: only its own weight copy lands here
+            mbar_init(full0 + 8 * s, rank == 0 ? 2 * PROD_WARPS + 1 : 1);
             mbar_init(empty0 + 8 * s, 1);  // one tcgen05.commit
         }
         mbar_init(accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == PROD_WARPS) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u)
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u)
                      : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();      // both CTAs' mbarriers are initialised and TMEM allocated before any remote arrive / MMA
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int nchunks = m.kchunks;
-    const uint32_t b_half_bytes = (uint32_t)bn * BK * 2;
+    const int hb = bn / 2;                                   // B rows held by each CTA of the pair
+    const uint32_t b_half_bytes = (uint32_t)hb * BK * 2;     // one bf16 image (hi or lo) of this CTA's B rows
 
     if (warp < PROD_WARPS) {
         // ------------------------------------------------------------ A producers
@@ -209,46 +244,39 @@ linear_tc_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda, 
         // chunk c+1 are issued BEFORE chunk c is converted and stored: their latency hides behind
         // the stage wait, the conversion and the shared-memory stores of the current chunk.
         const bool relu_in = flags & O4D_RELU_IN;
-        // lane -> (row rr of the 8-row group, quarter p): floats [4p, 4p+4) and [16+4p, 16+4p+4) of the row's
-        // 32-float chunk, so every LDG.128 of the warp covers 8 rows x 64 contiguous bytes = 16 FULL sectors.
-        // (The earlier mapping -- 8 consecutive floats per lane -- used half of each 32-byte sector per
-        // instruction; an ablation showed the main loop at 36 k cycles with and 15 k without the A loads,
-        // independent of warps / CTAs per SM, i.e. bound by outstanding L1 sector requests.)
-        const int rr = lane >> 2, pq = lane & 3;
+        const int kc = lane >> 3, rr = lane & 7;
         constexpr int GPW = (BM / 8) / PROD_WARPS;      // 8-row groups per producer warp (2)
         auto load_chunk = [&](int c, float (&v)[GPW][8]) {
-            const int gk0 = c * BK + pq * 4, gk1 = gk0 + 16;
+            const int gk = c * BK + kc * 8;
 #pragma unroll
             for (int g = 0; g < GPW; ++g) {
                 const int64_t grow = row0 + (warp * GPW + g) * 8 + rr;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[g][i] = 0.f;
                 if (grow < rows) {
-                    const float* src = A + grow * lda + gk0;
-                    if (gk1 + 4 <= k && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+                    const float* src = A + grow * lda + gk;
+                    if (gk + 8 <= k && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
                         const float4 p0 = *reinterpret_cast<const float4*>(src);
-                        const float4 p1 = *reinterpret_cast<const float4*>(src + 16);
+                        const float4 p1 = *reinterpret_cast<const float4*>(src + 4);
                         v[g][0] = p0.x; v[g][1] = p0.y; v[g][2] = p0.z; v[g][3] = p0.w;
                         v[g][4] = p1.x; v[g][5] = p1.y; v[g][6] = p1.z; v[g][7] = p1.w;
                     } else {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            if (gk0 + i < k) v[g][i] = src[i];
-                            if (gk1 + i < k) v[g][4 + i] = src[16 + i];
-                        }
+                        for (int i = 0; i < 8; ++i)
+                            if (gk + i < k) v[g][i] = src[i];
                     }
                 }
             }
         };
         float cur[GPW][8], nxt[GPW][8];
         const bool dbg = (blockIdx.x == gridDim.x / 2) && blockIdx.y == 0 && threadIdx.x == 0;
-        if (dbg) g_dbg_tc[0] = clock64();
+        if (dbg) g_dbg_tc2[0] = clock64();
         load_chunk(0, cur);
         for (int c = 0; c < nchunks; ++c) {
             const int s = c % STAGES;
             const uint32_t ph = (uint32_t)(c / STAGES) & 1u;
             if (c + 1 < nchunks) load_chunk(c + 1, nxt);
-            mbar_wait(empty0 + 8 * s, ph ^ 1u);
+            mbar_wait_cl(empty0 + 8 * s, ph ^ 1u);
             uint8_t* a_hi = smem + s * STAGE_BYTES;
             uint8_t* a_lo = a_hi + A_HALF_BYTES;
 #pragma unroll
@@ -261,17 +289,21 @@ linear_tc_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda, 
                     float x = relu_in ? fmaxf(cur[g][i], 0.f) : cur[g][i];
                     split_bf16(x, h[i], l[i]);
                 }
-                // [kc][row group][row][16 B]: floats 4p..4p+3 are half (p & 1) of core-matrix line kc = p >> 1,
-                // floats 16+4p.. the same half of line kc + 2
-                const int off = (pq >> 1) * (BM * 16) + rg * 128 + rr * 16 + (pq & 1) * 8;
-                *reinterpret_cast<uint2*>(a_hi + off) = *reinterpret_cast<const uint2*>(h);
-                *reinterpret_cast<uint2*>(a_lo + off) = *reinterpret_cast<const uint2*>(l);
-                *reinterpret_cast<uint2*>(a_hi + off + 2 * (BM * 16)) = *reinterpret_cast<const uint2*>(h + 4);
-                *reinterpret_cast<uint2*>(a_lo + off + 2 * (BM * 16)) = *reinterpret_cast<const uint2*>(l + 4);
+                const int off = kc * (BM * 16) + rg * 128 + rr * 16;   // [kc][row group][row][16 B]
+                *reinterpret_cast<uint4*>(a_hi + off) = *reinterpret_cast<const uint4*>(h);
+                *reinterpret_cast<uint4*>(a_lo + off) = *reinterpret_cast<const uint4*>(l);
             }
             fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
             __syncwarp();
-            if (lane == 0) mbar_arrive(full0 + 8 * s);
+            if (lane == 0) {
+                if (rank == 0) {
+                    mbar_arrive(full0 + 8 * s);
+                } else {
+                    // the peer's warp 0 also waits for the peer's own weight half before vouching for the stage
+                    if (warp == 0) mbar_wait(full0 + 8 * s, ph);
+                    mbar_arrive_cluster(full0 + 8 * s, 0);
+                }
+            }
 #pragma unroll
             for (int g = 0; g < GPW; ++g)
 #pragma unroll
@@ -284,10 +316,10 @@ linear_tc_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda, 
         // stages are idle by now): in the write phase a lane owns one COLUMN, so every load of
         // the residual and every store of C is one contiguous 128-byte row segment, and the loads
         // of eight rows are issued back to back before they are consumed.
-        if (dbg) g_dbg_tc[1] = clock64();
-        mbar_wait(accum_bar, 0);
+        if (dbg) g_dbg_tc2[1] = clock64();
+        mbar_wait_cl(accum_bar, 0);
         tc_fence_after();
-        if (dbg) g_dbg_tc[2] = clock64();
+        if (dbg) g_dbg_tc2[2] = clock64();
         const bool relu_out = flags & O4D_RELU_OUT;
         const int quarter = warp & 3, chalf = warp >> 2;
         const int64_t warp_row0 = row0 + quarter * 32;
@@ -373,30 +405,32 @@ linear_tc_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda, 
                 }
             }
         }
-        if (dbg) g_dbg_tc[3] = clock64();
+        if (dbg) g_dbg_tc2[3] = clock64();
         tc_fence_before();
     } else if (warp == PROD_WARPS) {
         // ------------------------------------------------------------ weight slabs via the TMA engine
         if (lane == 0) {
-            const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(Wp) + (size_t)tile_n * nchunks * 2 * b_half_bytes;
+            // packed per (tile, chunk): [half 0 hi][half 0 lo][half 1 hi][half 1 lo]; this CTA takes half `rank`
+            const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(Wp) + (size_t)tile_n * nchunks * 4 * b_half_bytes +
+                                  (size_t)rank * 2 * b_half_bytes;
             for (int c = 0; c < nchunks; ++c) {
                 const int s = c % STAGES;
                 const uint32_t ph = (uint32_t)(c / STAGES) & 1u;
-                mbar_wait(empty0 + 8 * s, ph ^ 1u);
+                mbar_wait_cl(empty0 + 8 * s, ph ^ 1u);
                 const uint32_t dst = smem_base + s * STAGE_BYTES + 2 * A_HALF_BYTES;
                 mbar_arrive_expect_tx(full0 + 8 * s, 2 * b_half_bytes);
-                bulk_g2s(dst, wsrc + (size_t)c * 2 * b_half_bytes, 2 * b_half_bytes, full0 + 8 * s);
+                bulk_g2s(dst, wsrc + (size_t)c * 4 * b_half_bytes, 2 * b_half_bytes, full0 + 8 * s);
             }
         }
     } else {
         // ------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        if (lane == 0 && rank == 0) {
             const uint32_t idesc = umma_idesc(bn);
-            const uint32_t lbo_a = BM * 16, lbo_b = (uint32_t)bn * 16;
+            const uint32_t lbo_a = BM * 16, lbo_b = (uint32_t)hb * 16;
             for (int c = 0; c < nchunks; ++c) {
                 const int s = c % STAGES;
                 const uint32_t ph = (uint32_t)(c / STAGES) & 1u;
-                mbar_wait(full0 + 8 * s, ph);
+                mbar_wait_cl(full0 + 8 * s, ph);
                 tc_fence_after();
                 const uint32_t a_hi = smem_base + s * STAGE_BYTES;
                 const uint32_t a_lo = a_hi + A_HALF_BYTES;
@@ -420,84 +454,60 @@ linear_tc_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda, 
         }
     }
     __syncthreads();
+    cluster_sync_all();      // the peer's TMEM / shared memory stay valid until the leader's last MMA has retired
     if (warp == PROD_WARPS) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
     }
 }
 
-}  // namespace tc
+}  // namespace tc2
 
-// 2-CTA (cta_group::2) variant, gemm_tc2.cu.  O4D_TC_PAIR=0/1 selects it for every weight whose tile is at
-// least 32 columns wide; the packed-weight format differs (each CTA of a pair copies half of the tile's rows),
-// so packing and launching consult the same predicate.
-int tc2_pack_launch(const float* W, int64_t n, int64_t k, int64_t ldw, void* packed, cudaStream_t st);
-int linear_tc2_packed_launch(const float* A, int64_t rows, int64_t k, int64_t lda, const void* packed, int64_t n,
-                             const float* bias, const float* R, int64_t ldr, float* C, int64_t ldc, int flags,
-                             int precision, cudaStream_t st, const RowGather* gp);
-static bool tc_pair(int64_t n, int64_t k) {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("O4D_TC_PAIR");
-        v = (e && e[0] == '1') ? 1 : 0;
-    }
-    return v == 1 && tc::pack_meta((int)n, (int)k).bn >= 32;
-}
+size_t tc2_pack_bytes(int64_t n, int64_t k) { return tc2::pack_bytes(tc2::pack_meta((int)n, (int)k)); }
 
-size_t tc_pack_bytes(int64_t n, int64_t k) { return tc::pack_bytes(tc::pack_meta((int)n, (int)k)); }
-
-int tc_pack_launch(const float* W, int64_t n, int64_t k, int64_t ldw, void* packed, cudaStream_t st) {
-    if (tc_pair(n, k)) return tc2_pack_launch(W, n, k, ldw, packed, st);
-    tc::PackMeta m = tc::pack_meta((int)n, (int)k);
-    const int64_t total = (int64_t)m.ntiles * m.kchunks * m.bn * tc::BK;
+int tc2_pack_launch(const float* W, int64_t n, int64_t k, int64_t ldw, void* packed, cudaStream_t st) {
+    tc2::PackMeta m = tc2::pack_meta((int)n, (int)k);
+    const int64_t total = (int64_t)m.ntiles * m.kchunks * m.bn * tc2::BK;
     int64_t blocks = cdiv(total, 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
-    tc::pack_weight_kernel<<<(unsigned)blocks, 256, 0, st>>>(W, ldw, m, (__nv_bfloat16*)packed);
+    tc2::pack_weight_pair_kernel<<<(unsigned)blocks, 256, 0, st>>>(W, ldw, m, (__nv_bfloat16*)packed);
     O4D_LAUNCH_CHECK();
     return 0;
 }
 
-// n >= 8: narrow outputs (lin_out, 9 .. 33 columns) run as one 16/32/48-column UMMA tile; the CUDA-core kernel
-// took as long for 416 -> 9 as the tensor-core kernel for 416 -> 416 (69 us per 32768 rows).
-bool tc_shape_ok(int64_t rows, int64_t k, int64_t n) { return rows >= 1024 && k >= 32 && n >= 4 && k <= 65536 && n <= 65536; }
-
-int linear_tc_packed_launch(const float* A, int64_t rows, int64_t k, int64_t lda, const void* packed, int64_t n,
-                            const float* bias, const float* R, int64_t ldr, float* C, int64_t ldc, int flags,
-                            int precision, cudaStream_t st, const RowGather* gp) {
+int linear_tc2_packed_launch(const float* A, int64_t rows, int64_t k, int64_t lda, const void* packed, int64_t n,
+                             const float* bias, const float* R, int64_t ldr, float* C, int64_t ldc, int flags,
+                             int precision, cudaStream_t st, const RowGather* gp) {
     if (rows == 0) return 0;
-    if (tc_pair(n, k)) return linear_tc2_packed_launch(A, rows, k, lda, packed, n, bias, R, ldr, C, ldc, flags, precision, st, gp);
     RowGather g;
     if (gp) g = *gp;
     static bool attr_done = false;
     if (!attr_done) {
-        O4D_CUDA(cudaFuncSetAttribute(tc::linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+        O4D_CUDA(cudaFuncSetAttribute(tc2::linear_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
         attr_done = true;
     }
-    tc::PackMeta m = tc::pack_meta((int)n, (int)k);
-    dim3 grid((unsigned)cdiv(rows, tc::BM), (unsigned)m.ntiles);
-    tc::linear_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(A, rows, (int)k, lda, (const __nv_bfloat16*)packed, m, bias, R,
-                                                                    ldr, C, ldc, flags, precision == 1 ? 1 : 0, g);
-    O4D_LAUNCH_CHECK();
+    tc2::PackMeta m = tc2::pack_meta((int)n, (int)k);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(cdiv(cdiv(rows, tc2::BM), 2) * 2), (unsigned)m.ntiles, 1);   // row tiles in pairs
+    cfg.blockDim = dim3(tc2::THREADS, 1, 1);
+    cfg.dynamicSmemBytes = tc2::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const int split = precision == 1 ? 1 : 0;
+    O4D_CUDA(cudaLaunchKernelEx(&cfg, tc2::linear_tc2_kernel, A, rows, (int)k, lda, (const __nv_bfloat16*)packed, m, bias, R, ldr, C,
+                                ldc, flags, split, g));
+    count_launch();
     return 0;
-}
-
-// Un-packed entry: packs the weight into a stream-ordered temporary first (generic C-ABI
-// calls; the decoder keeps its weights packed in the scene buffer instead).
-int linear_tc_launch(const float* A, int64_t rows, int64_t k, int64_t lda, const float* W, const float* bias,
-                     int64_t n, const float* R, int64_t ldr, float* C, int64_t ldc, int flags, int precision,
-                     cudaStream_t st, const RowGather* g) {
-    if (!tc_shape_ok(rows, k, n)) return O4D_E_UNSUPPORTED;
-    void* packed = nullptr;
-    O4D_CUDA(cudaMallocAsync(&packed, tc_pack_bytes(n, k), st));
-    int rc = tc_pack_launch(W, n, k, k, packed, st);
-    if (rc == 0) rc = linear_tc_packed_launch(A, rows, k, lda, packed, n, bias, R, ldr, C, ldc, flags, precision, st, g);
-    cudaFreeAsync(packed, st);
-    return rc;
 }
 
 }  // namespace o4d
 
-extern "C" int o4d_has_tcgen05(void) { return 1; }
-extern "C" int o4d_debug_read_tc(long long* out16) {
-    return (int)cudaMemcpyFromSymbol(out16, o4d::tc::g_dbg_tc, sizeof(long long) * 16);
+extern "C" int o4d_debug_read_tc2(long long* out16) {
+    return (int)cudaMemcpyFromSymbol(out16, o4d::tc2::g_dbg_tc2, sizeof(long long) * 16);
 }

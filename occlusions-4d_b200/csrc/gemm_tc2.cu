@@ -244,26 +244,33 @@ linear_tc2_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda,
         // chunk c+1 are issued BEFORE chunk c is converted and stored: their latency hides behind
         // the stage wait, the conversion and the shared-memory stores of the current chunk.
         const bool relu_in = flags & O4D_RELU_IN;
-        const int kc = lane >> 3, rr = lane & 7;
+        // lane -> (row rr of the 8-row group, quarter p): floats [4p, 4p+4) and [16+4p, 16+4p+4) of the row's
+        // 32-float chunk, so every LDG.128 of the warp covers 8 rows x 64 contiguous bytes = 16 FULL sectors.
+        // (The earlier mapping -- 8 consecutive floats per lane -- used half of each 32-byte sector per
+        // instruction; an ablation showed the main loop at 36 k cycles with and 15 k without the A loads,
+        // independent of warps / CTAs per SM, i.e. bound by outstanding L1 sector requests.)
+        const int rr = lane >> 2, pq = lane & 3;
         constexpr int GPW = (BM / 8) / PROD_WARPS;      // 8-row groups per producer warp (2)
         auto load_chunk = [&](int c, float (&v)[GPW][8]) {
-            const int gk = c * BK + kc * 8;
+            const int gk0 = c * BK + pq * 4, gk1 = gk0 + 16;
 #pragma unroll
             for (int g = 0; g < GPW; ++g) {
                 const int64_t grow = row0 + (warp * GPW + g) * 8 + rr;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[g][i] = 0.f;
                 if (grow < rows) {
-                    const float* src = A + grow * lda + gk;
-                    if (gk + 8 <= k && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+                    const float* src = A + grow * lda + gk0;
+                    if (gk1 + 4 <= k && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
                         const float4 p0 = *reinterpret_cast<const float4*>(src);
-                        const float4 p1 = *reinterpret_cast<const float4*>(src + 4);
+                        const float4 p1 = *reinterpret_cast<const float4*>(src + 16);
                         v[g][0] = p0.x; v[g][1] = p0.y; v[g][2] = p0.z; v[g][3] = p0.w;
                         v[g][4] = p1.x; v[g][5] = p1.y; v[g][6] = p1.z; v[g][7] = p1.w;
                     } else {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            if (gk + i < k) v[g][i] = src[i];
+                        for (int i = 0; i < 4; ++i) {
+                            if (gk0 + i < k) v[g][i] = src[i];
+                            if (gk1 + i < k) v[g][4 + i] = src[16 + i];
+                        }
                     }
                 }
             }
@@ -289,9 +296,13 @@ linear_tc2_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda,
                     float x = relu_in ? fmaxf(cur[g][i], 0.f) : cur[g][i];
                     split_bf16(x, h[i], l[i]);
                 }
-                const int off = kc * (BM * 16) + rg * 128 + rr * 16;   // [kc][row group][row][16 B]
-                *reinterpret_cast<uint4*>(a_hi + off) = *reinterpret_cast<const uint4*>(h);
-                *reinterpret_cast<uint4*>(a_lo + off) = *reinterpret_cast<const uint4*>(l);
+                // [kc][row group][row][16 B]: floats 4p..4p+3 are half (p & 1) of core-matrix line kc = p >> 1,
+                // floats 16+4p.. the same half of line kc + 2
+                const int off = (pq >> 1) * (BM * 16) + rg * 128 + rr * 16 + (pq & 1) * 8;
+                *reinterpret_cast<uint2*>(a_hi + off) = *reinterpret_cast<const uint2*>(h);
+                *reinterpret_cast<uint2*>(a_lo + off) = *reinterpret_cast<const uint2*>(l);
+                *reinterpret_cast<uint2*>(a_hi + off + 2 * (BM * 16)) = *reinterpret_cast<const uint2*>(h + 4);
+                *reinterpret_cast<uint2*>(a_lo + off + 2 * (BM * 16)) = *reinterpret_cast<const uint2*>(l + 4);
             }
             fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
             __syncwarp();

@@ -212,6 +212,15 @@ int attn_core_launch(const PtBlockParams& P, const float* q, const AttnTables& T
     }
     if (P.w3 == nullptr) return 0;
     // z = x + W3 agg + b3   (modules.py:64-65)
+    if (T.w3cat) {   // decoder: layer3 K-concatenated with the next block's lin_z (second operand = local features)
+        RowGather cat;
+        cat.a2 = T.cat_a2;
+        cat.lda2 = T.cat_lda2;
+        cat.k2 = T.cat_k2;
+        const int64_t kc = (d + 31) / 32 * 32 + T.cat_k2;
+        O4D_TRY(linear_ps_launch(P.ps, agg, n, d, d, T.w3cat, kc, T.b3cat, d, x_res, d, out, d, 0, precision, st, &cat));
+        return 0;
+    }
     O4D_TRY(linear_ps_launch(P.ps, agg, n, d, d, P.w3, d, P.b3, d, x_res, d, out, d, 0, precision, st));
     return 0;
 }

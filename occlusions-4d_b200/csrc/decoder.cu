@@ -10,6 +10,16 @@
 
 namespace o4d {
 
+__global__ void vec_add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] + b[i];
+}
+static int vec_add_launch(const float* a, const float* b, float* out, int n, cudaStream_t st) {
+    vec_add_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(a, b, out, n);
+    O4D_LAUNCH_CHECK();
+    return 0;
+}
+
 static bool dec_cfg_ok(const o4d_decoder_config* c) {
     return c && c->d_in == 4 && c->d_hidden >= 1 && c->d_out >= 1 && c->d_latent == c->d_hidden &&
            c->d_latent_local >= 1 && c->d_latent_local < c->d_latent && c->n_blocks >= 1 &&
@@ -60,9 +70,20 @@ struct SceneView {
     float* bqa[O4D_MAX_BLOCKS];    // (2H)    = W_a1 W_q b_1 + cvec
     float* t1[O4D_MAX_BLOCKS];     // (H, H)  = W_q W_1 (scratch kept for the lifetime of the scene)
     float* t1b[O4D_MAX_BLOCKS];    // (H)     = W_q b_1
+    // lin_z folded into the layer that produces x (precision != 0):  for block i,
+    //   wcat[i] (H, kcat[i]) = [W_pred | 0 pad to 32 | W_z[i][:, Dg:]],  bcat[i] = b_pred + zg[i]
+    // with pred = lin_in (i = 0), layer3 of the cross layer after block i-1, or fc_1 of block i-1.
+    float* wcat[O4D_MAX_BLOCKS];
+    float* bcat[O4D_MAX_BLOCKS];
+    int kcat[O4D_MAX_BLOCKS];
     size_t pack_off;  // byte offset of the pre-packed tcgen05 weights (precision != 0)
     size_t bytes;
 };
+
+static int round32(int v) { return (v + 31) / 32 * 32; }
+static int pe_width(const o4d_decoder_config* c) {
+    return c->pos_encoding_freqs > 0 ? c->d_in * (2 * c->pos_encoding_freqs + 1) : c->d_in;
+}
 
 static size_t packed_total_bytes(const o4d_decoder_config* c);
 
@@ -89,6 +110,12 @@ static SceneView scene_view(const o4d_decoder_config* c, int64_t m, void* base) 
         s.t1[j] = a.get<float>((size_t)c->d_hidden * c->d_hidden);
         s.t1b[j] = a.get<float>((size_t)c->d_hidden);
     }
+    for (int b = 0; b < c->n_blocks; ++b) {
+        const int k1 = b == 0 ? pe_width(c) : c->d_hidden;
+        s.kcat[b] = round32(k1) + c->d_latent_local;
+        s.wcat[b] = a.get<float>((size_t)c->d_hidden * s.kcat[b]);
+        s.bcat[b] = a.get<float>((size_t)c->d_hidden);
+    }
     s.pack_off = a.off;
     a.get<char>(packed_total_bytes(c));
     s.bytes = a.off;
@@ -108,6 +135,10 @@ static void for_each_tc_weight(const o4d_decoder_config* c, const DecParams& d, 
     const int pe_w = c->pos_encoding_freqs > 0 ? c->d_in * (2 * c->pos_encoding_freqs + 1) : c->d_in;
     fn(d.lin_in_w, H, pe_w, pe_w);
     fn(d.lin_out_w, c->d_out, H, H);
+    for (int b = 0; b < c->n_blocks; ++b) {       // K-concatenated [pred | lin_z local] weights
+        const int kc = round32(b == 0 ? pe_w : H) + E;
+        fn(s ? s->wcat[b] : nullptr, H, kc, kc);
+    }
     for (int b = 0; b < c->n_blocks; ++b) {
         fn(d.z_w[b] ? d.z_w[b] + Dg : nullptr, H, E, c->d_latent);  // local half of lin_z (column slice)
         fn(d.fc0_w[b], H, H, H);
@@ -176,6 +207,25 @@ int decoder_prepare(const o4d_decoder_config* c, const float* const* P, const fl
         O4D_TRY(matmul_nn_launch(pp.wa1, H, s.t1b[j], 1, T.cvec, s.bqa[j], 2 * H, H, 1, st));
     }
     if (c->precision != 0) {
+        // [W_pred | pad | W_z,local] and b_pred + zg for every block (see SceneView)
+        for (int b = 0; b < c->n_blocks; ++b) {
+            const float* wpred;
+            const float* bpred;
+            int k1;
+            if (b == 0) {
+                wpred = d.lin_in_w; bpred = d.lin_in_b; k1 = pe_width(c);
+            } else if (d.use_pt[b - 1] >= 0) {
+                wpred = d.pt[d.use_pt[b - 1]][13]; bpred = d.pt[d.use_pt[b - 1]][14]; k1 = H;
+            } else {
+                wpred = d.fc1_w[b - 1]; bpred = d.fc1_b[b - 1]; k1 = H;
+            }
+            const int kc = s.kcat[b];
+            O4D_CUDA(cudaMemsetAsync(s.wcat[b], 0, (size_t)H * kc * sizeof(float), st));
+            O4D_TRY(copy2d_launch(wpred, k1, H, k1, s.wcat[b], kc, st));
+            O4D_TRY(copy2d_launch(d.z_w[b] + Dg, c->d_latent, H, E, s.wcat[b] + round32(k1), kc, st));
+            // bcat = 1 * bpred + zg[b]  (a 1-row dense layer with the identity-free trick: copy then add)
+            O4D_TRY(vec_add_launch(bpred, s.zg + (size_t)b * H, s.bcat[b], H, st));
+        }
         // bf16 hi/lo shared-memory images of every weight the tcgen05 path reads
         char* p = (char*)scene + s.pack_off;
         int rc = 0;
@@ -243,20 +293,35 @@ int decoder_forward(const o4d_decoder_config* c, const float* const* P, const vo
     // point_transformer_layer.py:167 -- identical for every cross layer (same query / abstract cloud)
     if (c->cross_attn_layers > 0)
         O4D_TRY(knn_launch(query, nq, c->d_in, s.abs_xyz, m, 3, c->cross_attn_neighbors, 0, w.idx_c, nullptr, nullptr, st));
-    // implicit.py:403-408
-    if (c->pos_encoding_freqs > 0) {
-        O4D_TRY(posenc_launch(query, nq, c->d_in, c->pos_encoding_freqs, w.pe, st));
-        O4D_TRY(linear_ps_launch(&ps, w.pe, nq, pe_w, pe_w, d.lin_in_w, pe_w, d.lin_in_b, H, nullptr, 0, w.x, H, 0, prec, st));
-    } else {
-        O4D_TRY(linear_ps_launch(&ps, query, nq, c->d_in, c->d_in, d.lin_in_w, c->d_in, d.lin_in_b, H, nullptr, 0, w.x, H, 0, prec, st));
-    }
+    // lin_z folded into the producing layer whenever the packed K-concatenated weights exist
+    const bool fold = prec != 0 && ps.find(s.wcat[0]) != nullptr && tc_shape_ok(nq, H, H) &&
+                      tc_shape_ok(nq, c->pos_encoding_freqs > 0 ? pe_w : c->d_in, H);
+    RowGather cat;
+    cat.a2 = w.f_loc;
+    cat.lda2 = E;
+    cat.k2 = E;
+    // implicit.py:403-408 (+ :416-418 of block 0 when folded)
+    const float* in_ptr = c->pos_encoding_freqs > 0 ? w.pe : query;
+    const int in_w = c->pos_encoding_freqs > 0 ? pe_w : c->d_in;
+    if (c->pos_encoding_freqs > 0) O4D_TRY(posenc_launch(query, nq, c->d_in, c->pos_encoding_freqs, w.pe, st));
+    if (fold)
+        O4D_TRY(linear_ps_launch(&ps, in_ptr, nq, in_w, in_w, s.wcat[0], s.kcat[0], s.bcat[0], H, nullptr, 0, w.x, H, 0,
+                                 prec, st, &cat));
+    else
+        O4D_TRY(linear_ps_launch(&ps, in_ptr, nq, in_w, in_w, d.lin_in_w, in_w, d.lin_in_b, H, nullptr, 0, w.x, H, 0, prec, st));
     for (int b = 0; b < c->n_blocks; ++b) {
         // implicit.py:416-418  x += lin_z(features_query)   (global half pre-reduced into zg)
-        O4D_TRY(linear_ps_launch(&ps, w.f_loc, nq, E, E, d.z_w[b] + Dg, c->d_latent, s.zg + (size_t)b * H, H, w.x, H,
-                                 w.x, H, 0, prec, st));
+        if (!fold)
+            O4D_TRY(linear_ps_launch(&ps, w.f_loc, nq, E, E, d.z_w[b] + Dg, c->d_latent, s.zg + (size_t)b * H, H, w.x, H,
+                                     w.x, H, 0, prec, st));
+        const bool fold_next = fold && b + 1 < c->n_blocks;       // this block's last layer also adds lin_z[b+1]
         // implicit.py:93-101  x += fc_1(relu(fc_0(relu(x))))
         O4D_TRY(linear_ps_launch(&ps, w.x, nq, H, H, d.fc0_w[b], H, d.fc0_b[b], H, nullptr, 0, w.h, H, O4D_RELU_IN, prec, st));
-        O4D_TRY(linear_ps_launch(&ps, w.h, nq, H, H, d.fc1_w[b], H, d.fc1_b[b], H, w.x, H, w.x, H, O4D_RELU_IN, prec, st));
+        if (fold_next && d.use_pt[b] < 0)
+            O4D_TRY(linear_ps_launch(&ps, w.h, nq, H, H, s.wcat[b + 1], s.kcat[b + 1], s.bcat[b + 1], H, w.x, H, w.x, H,
+                                     O4D_RELU_IN, prec, st, &cat));
+        else
+            O4D_TRY(linear_ps_launch(&ps, w.h, nq, H, H, d.fc1_w[b], H, d.fc1_b[b], H, w.x, H, w.x, H, O4D_RELU_IN, prec, st));
         if (d.use_pt[b] >= 0) {
             // implicit.py:421-439 -> modules.py:61-65 cross attention onto the abstract cloud
             const int j = d.use_pt[b];
@@ -272,6 +337,13 @@ int decoder_forward(const o4d_decoder_config* c, const float* const* P, const vo
                 T.fused = s.fused[j];
                 T.wqa = s.wqa[j];
                 T.bqa = s.bqa[j];
+            }
+            if (fold_next) {                              // layer3 of this block also adds lin_z[b+1]
+                T.w3cat = s.wcat[b + 1];
+                T.b3cat = s.bcat[b + 1];
+                T.cat_a2 = w.f_loc;
+                T.cat_lda2 = E;
+                T.cat_k2 = E;
             }
             O4D_TRY(attn_core_launch(pp, w.x, T, query, c->d_in, s.abs_xyz, 3, w.idx_c, nq, H,
                                      c->cross_attn_neighbors, w.x, w.x, prec, w.sub, w.sub_bytes, st));

@@ -141,11 +141,17 @@ int linear_ldw_launch(const float* A, int64_t rows, int64_t k, int64_t lda, cons
 int linear_ps_launch(const PackedSet* ps, const float* A, int64_t rows, int64_t k, int64_t lda, const float* W,
                      int64_t ldw, const float* bias, int64_t n, const float* R, int64_t ldr, float* C,
                      int64_t ldc, int flags, int precision, cudaStream_t st, const RowGather* g) {
-    ProfScope prof(PROF_LINEAR, 2.0 * (double)rows * (double)k * (double)n, st);
+    ProfScope prof(PROF_LINEAR, 2.0 * (double)rows * (double)(k + (g ? g->k2 : 0)) * (double)n, st);
     if (precision != 0 && tc_shape_ok(rows, k, n)) {
         const void* packed = ps ? ps->find(W) : nullptr;
         if (packed)
             return linear_tc_packed_launch(A, rows, k, lda, packed, n, bias, R, ldr, C, ldc, flags, precision, st, g);
+    }
+    if (g && g->a2) {
+        set_error("linear: a K-concatenated second operand needs the tcgen05 path with a pre-packed weight");
+        return O4D_E_UNSUPPORTED;
+    }
+    if (precision != 0 && tc_shape_ok(rows, k, n)) {
         if (ldw == k) {
             int rc = linear_tc_launch(A, rows, k, lda, W, bias, n, R, ldr, C, ldc, flags, precision, st, g);
             if (rc != O4D_E_UNSUPPORTED) return rc;

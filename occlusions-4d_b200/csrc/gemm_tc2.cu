@@ -251,25 +251,30 @@ linear_tc2_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda,
         // independent of warps / CTAs per SM, i.e. bound by outstanding L1 sector requests.)
         const int rr = lane >> 2, pq = lane & 3;
         constexpr int GPW = (BM / 8) / PROD_WARPS;      // 8-row groups per producer warp (2)
+        const int k1c = (k + BK - 1) / BK;              // chunks fed by A; the rest (if any) by the K-concatenated g.a2
         auto load_chunk = [&](int c, float (&v)[GPW][8]) {
-            const int gk0 = c * BK + pq * 4, gk1 = gk0 + 16;
+            const bool second = c >= k1c;
+            const float* Ab = second ? g.a2 : A;
+            const int64_t ldab = second ? g.lda2 : lda;
+            const int kk = second ? g.k2 : k;
+            const int gk0 = (second ? c - k1c : c) * BK + pq * 4, gk1 = gk0 + 16;
 #pragma unroll
-            for (int g = 0; g < GPW; ++g) {
-                const int64_t grow = row0 + (warp * GPW + g) * 8 + rr;
+            for (int gi = 0; gi < GPW; ++gi) {
+                const int64_t grow = row0 + (warp * GPW + gi) * 8 + rr;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[g][i] = 0.f;
+                for (int i = 0; i < 8; ++i) v[gi][i] = 0.f;
                 if (grow < rows) {
-                    const float* src = A + grow * lda + gk0;
-                    if (gk1 + 4 <= k && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+                    const float* src = Ab + grow * ldab + gk0;
+                    if (gk1 + 4 <= kk && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
                         const float4 p0 = *reinterpret_cast<const float4*>(src);
                         const float4 p1 = *reinterpret_cast<const float4*>(src + 16);
-                        v[g][0] = p0.x; v[g][1] = p0.y; v[g][2] = p0.z; v[g][3] = p0.w;
-                        v[g][4] = p1.x; v[g][5] = p1.y; v[g][6] = p1.z; v[g][7] = p1.w;
+                        v[gi][0] = p0.x; v[gi][1] = p0.y; v[gi][2] = p0.z; v[gi][3] = p0.w;
+                        v[gi][4] = p1.x; v[gi][5] = p1.y; v[gi][6] = p1.z; v[gi][7] = p1.w;
                     } else {
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                            if (gk0 + i < k) v[g][i] = src[i];
-                            if (gk1 + i < k) v[g][4 + i] = src[16 + i];
+                            if (gk0 + i < kk) v[gi][i] = src[i];
+                            if (gk1 + i < kk) v[gi][4 + i] = src[16 + i];
                         }
                     }
                 }
@@ -291,9 +296,10 @@ linear_tc2_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda,
                 const int rg = warp * GPW + g;                // 8-row group inside the 128-row tile
                 __align__(16) __nv_bfloat16 h[8];
                 __align__(16) __nv_bfloat16 l[8];
+                const bool relu_c = relu_in && c < k1c;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    float x = relu_in ? fmaxf(cur[g][i], 0.f) : cur[g][i];
+                    float x = relu_c ? fmaxf(cur[g][i], 0.f) : cur[g][i];
                     split_bf16(x, h[i], l[i]);
                 }
                 // [kc][row group][row][16 B]: floats 4p..4p+3 are half (p & 1) of core-matrix line kc = p >> 1,
@@ -497,7 +503,8 @@ int linear_tc2_packed_launch(const float* A, int64_t rows, int64_t k, int64_t ld
         O4D_CUDA(cudaFuncSetAttribute(tc2::linear_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
         attr_done = true;
     }
-    tc2::PackMeta m = tc2::pack_meta((int)n, (int)k);
+    const int64_t ktot = g.a2 ? cdiv(k, tc2::BK) * tc2::BK + g.k2 : k;   // K-concatenated second operand
+    tc2::PackMeta m = tc2::pack_meta((int)n, (int)ktot);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(cdiv(cdiv(rows, tc2::BM), 2) * 2), (unsigned)m.ntiles, 1);   // row tiles in pairs
     cfg.blockDim = dim3(tc2::THREADS, 1, 1);

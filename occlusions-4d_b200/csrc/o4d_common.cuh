@@ -89,6 +89,13 @@ struct RowGather {
     const int32_t* nbr = nullptr;
     int knbr = 1;
     int64_t row_offset = 0;
+    // Optional SECOND A operand, concatenated along K behind the first one (tcgen05 path with a
+    // pre-packed weight only):  C = post(pre(A) W[:, :k1p]^T + A2 W[:, k1p:]^T + bias) [+ R],
+    // k1p = k rounded up to 32.  O4D_RELU_IN applies to A only.  Used to fold every lin_z of the
+    // decoder (x += W_z f_local) into the layer that produces x.
+    const float* a2 = nullptr;
+    int64_t lda2 = 0;
+    int k2 = 0;
 };
 
 // ---- internal launchers shared between translation units (all async on `st`) ----
@@ -162,6 +169,12 @@ struct AttnTables {
     //   Qa = (W_a1 W_q W_1) x + (W_a1 W_q b_1 + cvec);  when set, attn_core takes x instead of q
     const float* wqa = nullptr;
     const float* bqa = nullptr;
+    // optional K-concatenated layer3 (decoder): [W_3 | W_z,local of the next block], b_3 + zg, second operand
+    const float* w3cat = nullptr;
+    const float* b3cat = nullptr;
+    const float* cat_a2 = nullptr;
+    int64_t cat_lda2 = 0;
+    int cat_k2 = 0;
 };
 bool attn_fused_supported(int d, int k);
 size_t attn_fused_pack_bytes(int d);

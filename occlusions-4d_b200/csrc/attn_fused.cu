@@ -31,7 +31,7 @@ namespace fa {
 constexpr int BM = 128;
 constexpr int HC = 32;          // hidden units per chunk == K of the second contraction per chunk
 constexpr int ROW_WARPS = 8;    // two warps per TMEM lane quarter
-constexpr int THREADS = (ROW_WARPS + 2) * 32;
+constexpr int THREADS = (ROW_WARPS + 3) * 32;   // 8 row warps, weight-stream warp, MMA2 issuer, MMA1 / delta issuer
 constexpr int R_BYTES = BM * 32 * 2;         // one bf16 image of a (128 x 32) A operand
 constexpr int NBUF = 3;                      // acc1 (TMEM) / hidden A2 (smem) buffers: MMA1 runs two chunks ahead
 constexpr int WC_STAGES = 4;                 // ring of Wc chunks (4 KB each)
@@ -114,6 +114,21 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// A operand from tensor memory (lane = row, two bf16 per 32-bit column), B from shared memory
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+                 "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t mbar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
 }
@@ -370,10 +385,29 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fused_kernel(const Params p) 
             float h[16];
 #pragma unroll
             for (int e = 0; e < 16; ++e) h[e] = fmaxf(__uint_as_float(acc[e]) + qk[e], 0.f);
-            mbar_wait(BAR(A2_EMPTY + b), (use & 1u) ^ 1u);     // MMA2 of chunk c-NBUF has released the buffer
-            uint8_t* a2 = smem + OFF_A2 + b * 2 * R_BYTES;
-            store_a_half_row(a2, a2 + R_BYTES, r, half, h);
-            fence_proxy_async_smem();
+            // The hidden chunk goes back into the SAME tensor-memory columns acc1[b] came from, as the A
+            // operand of MMA2 (bf16 hi / lo, two values per 32-bit column): this thread read columns
+            // [16*half, 16*half+16) of the buffer and overwrites them with [hi (8 columns) | lo (8 columns)]
+            // of its 16 hidden units = one K=16 step.  The main loop was shared-memory-bandwidth bound
+            // (~239 KB per chunk at 128 B/cycle: every one of the 12 MMA2 instructions re-read a 4 KB A
+            // slab plus 6.6 KB of weights); A from TMEM removes 49 KB of reads and 16 KB of stores per chunk.
+            // No "buffer empty" wait: ACC1_FULL(c) means MMA1(c) has retired, and the tensor pipe runs in
+            // issue order, so MMA2(c - NBUF), the last reader of these columns, retired before it.
+            {
+                uint32_t whi[8], wlo[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    __nv_bfloat16 h0, l0, h1, l1;
+                    split_bf16(h[2 * e], h0, l0);
+                    split_bf16(h[2 * e + 1], h1, l1);
+                    whi[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                    wlo[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                }
+                const uint32_t ta = taddr + ACC1_COL + b * 32 + half * 16;
+                tmem_st8(ta, whi);
+                tmem_st8(ta + 8, wlo);
+                tmem_st_wait();
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(A2_FULL + b));
@@ -518,12 +552,54 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fused_kernel(const Params p) 
             }
         }
     } else {
-        // ================================================================== MMA issuer
+        // ================================================================== MMA issuers
+        // Two issuing threads.  With a single one the loop was bound by that thread: per chunk
+        // ~1080 cycles inside the MMA2 issue + commits (back-pressured by the tensor pipe), ~420 in the
+        // MMA1 issue + commits, ~460 in three mbarrier waits, all serial (in-kernel stamps: 51.7 k of the
+        // 48.7 k loop).  Warp 9 issues MMA2 only; warp 10 issues MMA1 (and the delta contractions of the
+        // epilogue) and runs ahead.  Cross-thread ordering is explicit: MMA1(c) overwrites acc1[c % 3],
+        // which MMA2(c - 3) read as its A operand, so warp 10 waits on A2_EMPTY (committed by warp 9).
         // Shared-memory descriptors are loop invariant per (buffer, k-step, hi/lo, n-tile); the
         // addresses differ only in the 14-bit start field, so every descriptor is a constant
         // base plus a small per-buffer offset.
-        if (lane == 0) {
-            const uint32_t idesc32 = umma_idesc(32), idescN = umma_idesc(dn);
+        if (lane == 0 && warp == ROW_WARPS + 1) {
+            const uint32_t idescN = umma_idesc(dn);
+            const uint32_t lbo_b = (uint32_t)d * 16;
+            const int split = p.split;
+            const uint64_t dw0 = umma_desc(smem_base + OFF_W, lbo_b, 128);         // W stage 0, hi, n-tile 0, ks 0
+            // logits += hidden[c % NBUF] . W_a2[c]^T  (K = 32, N = dn per n-tile); hidden (A) sits in tensor
+            // memory: per K=16 step [hi: 8 columns | lo: 8 columns] inside the acc1 buffer's 32 columns
+            auto mma2 = [&](int c) {
+                const uint32_t abase = tmem_base + ACC1_COL + (c % NBUF) * 32;
+                const uint64_t wbase = dw0 + (uint64_t)(((c & 1) * w2) >> 4);
+                for (int t = 0; t < ntile; ++t) {
+                    const uint32_t dcol = tmem_base + t * dn;
+                    const uint64_t wt = wbase + (uint64_t)(((t * dn / 8) * 128) >> 4);
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) {
+                        const uint32_t a_hi = abase + ks * 16;
+                        const uint32_t a_lo = a_hi + 8;
+                        const uint64_t w_hi = wt + (uint64_t)((ks * 2 * lbo_b) >> 4);
+                        const uint64_t w_lo = w_hi + (uint64_t)((d * 64) >> 4);
+                        umma_f16_ts(dcol, a_hi, w_hi, idescN, (c | ks) ? 1u : 0u);
+                        if (split) {
+                            umma_f16_ts(dcol, a_lo, w_hi, idescN, 1u);
+                            umma_f16_ts(dcol, a_hi, w_lo, idescN, 1u);
+                        }
+                    }
+                }
+            };
+            for (int c = 0; c < NC; ++c) {
+                mbar_wait(BAR(A2_FULL + c % NBUF), (uint32_t)(c / NBUF) & 1u);
+                mbar_wait(BAR(W_FULL + (c & 1)), (uint32_t)(c >> 1) & 1u);
+                tc_fence_after();
+                mma2(c);
+                umma_commit(BAR(W_EMPTY + (c & 1)));
+                umma_commit(BAR(A2_EMPTY + c % NBUF));          // acc1[c % 3] may be overwritten by MMA1(c + 3)
+            }
+            umma_commit(BAR(ACC2_FULL));
+        } else if (lane == 0 && warp == ROW_WARPS + 2) {
+            const uint32_t idesc32 = umma_idesc(32);
             const uint32_t lbo_a = BM * 16, lbo_b = (uint32_t)d * 16;
             const int split = p.split;
             uint64_t dr_hi[2], dr_lo[2];
@@ -533,8 +609,6 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fused_kernel(const Params p) 
                 dr_lo[ks] = umma_desc(smem_base + OFF_R + R_BYTES + ks * 2 * lbo_a, lbo_a, 128);
             }
             const uint64_t dc0 = umma_desc(smem_base + OFF_WC, 512, 128);          // Wc ring slot 0, hi, ks 0
-            const uint64_t da0 = umma_desc(smem_base + OFF_A2, lbo_a, 128);        // A2 buffer 0, hi, ks 0
-            const uint64_t dw0 = umma_desc(smem_base + OFF_W, lbo_b, 128);         // W stage 0, hi, n-tile 0, ks 0
             // acc1[c % NBUF] = r . Wc[c]^T  (K = 32, N = 32)
             auto mma1 = [&](int c) {
                 const uint32_t dcol = tmem_base + ACC1_COL + (c % NBUF) * 32;
@@ -550,50 +624,21 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fused_kernel(const Params p) 
                     }
                 }
             };
-            // logits += hidden[c % NBUF] . W_a2[c]^T  (K = 32, N = dn per n-tile)
-            auto mma2 = [&](int c) {
-                const uint64_t abase = da0 + (uint64_t)(((c % NBUF) * 2 * R_BYTES) >> 4);
-                const uint64_t wbase = dw0 + (uint64_t)(((c & 1) * w2) >> 4);
-                for (int t = 0; t < ntile; ++t) {
-                    const uint32_t dcol = tmem_base + t * dn;
-                    const uint64_t wt = wbase + (uint64_t)(((t * dn / 8) * 128) >> 4);
-#pragma unroll
-                    for (int ks = 0; ks < 2; ++ks) {
-                        const uint64_t a_hi = abase + (uint64_t)((ks * 2 * lbo_a) >> 4);
-                        const uint64_t a_lo = a_hi + (uint64_t)(R_BYTES >> 4);
-                        const uint64_t w_hi = wt + (uint64_t)((ks * 2 * lbo_b) >> 4);
-                        const uint64_t w_lo = w_hi + (uint64_t)((d * 64) >> 4);
-                        umma_f16(dcol, a_hi, w_hi, idescN, (c | ks) ? 1u : 0u);
-                        if (split) {
-                            umma_f16(dcol, a_lo, w_hi, idescN, 1u);
-                            umma_f16(dcol, a_hi, w_lo, idescN, 1u);
-                        }
-                    }
-                }
-            };
-            auto issue_mma1 = [&](int c) {
+            mbar_wait(BAR(R_READY), 0);
+            tc_fence_after();
+            for (int c = 0; c < NC; ++c) {
                 mbar_wait(BAR(WC_FULL + c % WC_STAGES), (uint32_t)(c / WC_STAGES) & 1u);
+                if (c >= NBUF) mbar_wait(BAR(A2_EMPTY + c % NBUF), (uint32_t)(c / NBUF - 1) & 1u);   // MMA2(c - 3) retired
                 tc_fence_after();
                 mma1(c);
                 umma_commit(BAR(ACC1_FULL + c % NBUF));
                 umma_commit(BAR(WC_EMPTY + c % WC_STAGES));
-            };
-            mbar_wait(BAR(R_READY), 0);
-            tc_fence_after();
-            issue_mma1(0);
-            if (NC > 1) issue_mma1(1);
-            for (int c = 0; c < NC; ++c) {
-                // acc1[(c+2) % 3] was last used by chunk c-1, drained before MMA2(c-1) was issued
-                if (c + 2 < NC) issue_mma1(c + 2);
-                mbar_wait(BAR(A2_FULL + c % NBUF), (uint32_t)(c / NBUF) & 1u);
-                mbar_wait(BAR(W_FULL + (c & 1)), (uint32_t)(c >> 1) & 1u);
-                tc_fence_after();
-                mma2(c);
-                umma_commit(BAR(W_EMPTY + (c & 1)));
-                umma_commit(BAR(A2_EMPTY + c % NBUF));
             }
-            umma_commit(BAR(ACC2_FULL));
-            // delta chunks: acc1[g % 3] = r . W_p2[cc*32 .. +32]^T   (g = NC + cc continues the buffer ring)
+            // delta chunks: acc1[g % 3] = r . W_p2[cc*32 .. +32]^T   (g = NC + cc continues the buffer ring).
+            // This thread runs ahead of the MMA2 issuer, and a parity wait only distinguishes adjacent phases
+            // of W_FULL[0]: first wait until every MMA2 has retired (so all W_a2 phases of the stage are
+            // over), then for the W_p2 image.
+            mbar_wait(BAR(ACC2_FULL), 0);
             mbar_wait(BAR(W_FULL + 0), (uint32_t)(NC >> 1) & 1u);
             tc_fence_after();
             const uint64_t dp_hi0 = umma_desc(smem_base + OFF_W, lbo_b, 128);
@@ -604,10 +649,13 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fused_kernel(const Params p) 
                 const int g = NC + cc;
                 const int b = g % NBUF;
                 const uint32_t use = (uint32_t)(g / NBUF);
-                if (use > 0) {                                   // previous contents of acc1[b] were drained
+                if (g - NBUF < NC) {
+                    // the buffer's previous user was a main-loop chunk: MMA2(g - 3) read it as A
+                    if (g >= NBUF) mbar_wait(BAR(A2_EMPTY + b), (uint32_t)(g / NBUF - 1) & 1u);
+                } else if (use > 0) {                            // a delta chunk: its acc1[b] was drained by the row warps
                     mbar_wait(BAR(A2_FULL + b), (use - 1u) & 1u);
-                    tc_fence_after();
                 }
+                tc_fence_after();
                 const uint32_t dcol = tmem_base + ACC1_COL + b * 32;
                 const uint64_t adv = (uint64_t)(cc * 512 >> 4);  // 32 rows further down the W_p2 image
                 umma_f16(dcol, dr_hi[0], dp_hi0 + adv, idesc32, 0u);

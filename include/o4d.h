@@ -39,6 +39,7 @@ extern "C" {
 
 #define O4D_MAX_K 16        /* largest neighbour count (pt_num_neighbors<=16) */
 #define O4D_MAX_BLOCKS 16   /* largest n_blocks / down_blocks accepted */
+#define O4D_MAX_OUT 64      /* largest d_out handled by o4d_output_activation_f32 */
 
 const char* o4d_last_error(void);
 /* ABI version of this header; bumped on any signature change. */
@@ -309,6 +310,22 @@ int o4d_layernorm_relu_backward_f32(const float* y, const float* dout, int64_t r
 /* Mean over points (model.py:189) and its gradient (dmean / rows broadcast to every row). */
 int o4d_col_mean_f32(const float* x, int64_t rows, int d, float* out, void* stream);
 int o4d_col_mean_backward_f32(const float* dmean, int64_t rows, int d, float* dx, void* stream);
+
+/* ================================================================== inference driver pieces
+ * (the caller's loop eval/inference.py:175-248 around the decoder.)
+ *
+ * Test-time query lattice of utils/geometry.py:1246-1262 ('grid' mode) generated on the device,
+ * bit-identical to the numpy code: counts = ceil(cbrt(num / volume) * extent) per axis (computed by
+ * o4d_grid_query_count, which returns the total and fills counts3), coordinate =
+ * (index + 0.5) * (extent / count) + lo in fp32 without FMA, x slowest / z fastest, t = time_idx.
+ *   out (total, 4) fp32 device, 16-byte aligned. */
+int64_t o4d_grid_query_count(int64_t num_sample, const double* extent3, int32_t* counts3_out);
+int o4d_grid_queries_f32(const int32_t* counts3, const double* extent3, const double* lo3, float time_idx,
+                         float* out, void* stream);
+
+/* Output squashing of eval/inference.py:218-243, in place on the decoder output (n, g):
+ * col_ops_host[c] = 0 keep the logit, 1 sigmoid, 2 clamp to [0, 1]  (HOST array of g bytes). */
+int o4d_output_activation_f32(float* out, int64_t n, int g, const uint8_t* col_ops_host, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,6 +1,7 @@
 // Small bandwidth-bound kernels of the path: Fourier encoding, inverse-distance feature
 // blend, neighbourhood max-pool, LayerNorm+ReLU, row gathers, column mean.
 #include "o4d_common.cuh"
+#include <math.h>
 
 namespace o4d {
 
@@ -221,7 +222,75 @@ int widen_idx_launch(const int32_t* in, int64_t count, int64_t* out, cudaStream_
     return 0;
 }
 
+// ---- test-time query lattice, utils/geometry.py:1246-1262 ('grid' mode), generated on the device ----
+// numpy: axis = (arange(c, dtype=float32) + 0.5) * (ext / c) + lo with Python-float scalars, i.e. every
+// operation rounded to fp32 and no FMA; meshgrid(indexing='ij') + ravel => x slowest, z fastest.
+__global__ void grid_queries_kernel(int cx, int cy, int cz, float sx, float sy, float sz, float lx, float ly, float lz,
+                                    float t, float* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t total = (int64_t)cx * cy * cz;
+    if (i >= total) return;
+    const int iz = (int)(i % cz);
+    const int iy = (int)((i / cz) % cy);
+    const int ix = (int)(i / ((int64_t)cz * cy));
+    float4 q;
+    q.x = __fadd_rn(__fmul_rn(__fadd_rn((float)ix, 0.5f), sx), lx);
+    q.y = __fadd_rn(__fmul_rn(__fadd_rn((float)iy, 0.5f), sy), ly);
+    q.z = __fadd_rn(__fmul_rn(__fadd_rn((float)iz, 0.5f), sz), lz);
+    q.w = t;
+    reinterpret_cast<float4*>(out)[i] = q;
+}
+
+// ---- output squashing of the inference loop, eval/inference.py:218-243, in place on (n, g) ----
+struct ColOps {
+    uint8_t op[O4D_MAX_OUT];   // 0 keep (logit), 1 sigmoid, 2 clamp to [0, 1]
+};
+__global__ void output_activation_kernel(float* __restrict__ out, int64_t n, int g, ColOps ops) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n * g) return;
+    const int c = (int)(e % g);
+    const float x = out[e];
+    if (ops.op[c] == 1) out[e] = 1.0f / (1.0f + expf(-x));
+    else if (ops.op[c] == 2) out[e] = fminf(fmaxf(x, 0.0f), 1.0f);
+}
+
 }  // namespace o4d
+
+extern "C" int64_t o4d_grid_query_count(int64_t num_sample, const double* extent3, int32_t* counts3_out) {
+    if (!extent3 || !counts3_out || num_sample < 1 || !(extent3[0] > 0 && extent3[1] > 0 && extent3[2] > 0)) return O4D_E_ARG;
+    const double per_unit = cbrt((double)num_sample / (extent3[0] * extent3[1] * extent3[2]));   // geometry.py:1248
+    int64_t total = 1;
+    for (int a = 0; a < 3; ++a) {
+        counts3_out[a] = (int32_t)ceil(per_unit * extent3[a]);
+        total *= counts3_out[a];
+    }
+    return total;
+}
+
+extern "C" int o4d_grid_queries_f32(const int32_t* counts3, const double* extent3, const double* lo3, float time_idx,
+                                    float* out, void* stream) {
+    O4D_REQUIRE(counts3 && extent3 && lo3 && out, "o4d_grid_queries_f32: null pointer");
+    O4D_REQUIRE(counts3[0] >= 1 && counts3[1] >= 1 && counts3[2] >= 1, "o4d_grid_queries_f32: empty lattice");
+    O4D_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "o4d_grid_queries_f32: output must be 16-byte aligned");
+    const int64_t total = (int64_t)counts3[0] * counts3[1] * counts3[2];
+    // (ext / c) and lo are Python floats in the reference: rounded to fp32 when they meet the fp32 array
+    o4d::grid_queries_kernel<<<(unsigned)o4d::cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        counts3[0], counts3[1], counts3[2], (float)(extent3[0] / counts3[0]), (float)(extent3[1] / counts3[1]),
+        (float)(extent3[2] / counts3[2]), (float)lo3[0], (float)lo3[1], (float)lo3[2], time_idx, out);
+    O4D_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int o4d_output_activation_f32(float* out, int64_t n, int g, const uint8_t* col_ops_host, void* stream) {
+    O4D_REQUIRE(out && col_ops_host && n >= 0 && g >= 1 && g <= O4D_MAX_OUT, "o4d_output_activation_f32: bad argument (g <= %d)",
+                O4D_MAX_OUT);
+    if (n == 0) return 0;
+    o4d::ColOps ops;
+    for (int c = 0; c < O4D_MAX_OUT; ++c) ops.op[c] = c < g ? col_ops_host[c] : 0;
+    o4d::output_activation_kernel<<<(unsigned)o4d::cdiv(n * g, 256), 256, 0, (cudaStream_t)stream>>>(out, n, g, ops);
+    O4D_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" int o4d_posenc_f32(const float* points, int64_t n, int d_in, int n_freq, float* out, void* stream) {
     O4D_REQUIRE(points && out && n >= 0 && d_in >= 1, "o4d_posenc_f32: bad argument");

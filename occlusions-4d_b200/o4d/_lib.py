@@ -88,6 +88,9 @@ SIGNATURES = {
                                                 c_ptr, c_ptr, c_ptr, c_ptr]),
     'o4d_col_mean_f32': (c_int, [c_ptr, c_i64, c_int, c_ptr, c_ptr]),
     'o4d_col_mean_backward_f32': (c_int, [c_ptr, c_i64, c_int, c_ptr, c_ptr]),
+    'o4d_grid_query_count': (c_i64, [c_i64, c_ptr, c_ptr]),
+    'o4d_grid_queries_f32': (c_int, [c_ptr, c_ptr, c_ptr, ctypes.c_float, c_ptr, c_ptr]),
+    'o4d_output_activation_f32': (c_int, [c_ptr, c_i64, c_int, c_ptr, c_ptr]),
 }
 
 _lib = None

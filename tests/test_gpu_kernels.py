@@ -240,3 +240,37 @@ def test_down_transition_matches_oracle(norm):
     assert torch.equal(gi.cpu(), fidx)
     assert torch.equal(gp.cpu(), pos_sub)
     assert relerr(gz.cpu(), z) < TOL_FP32
+
+
+# ------------------------------------------------------------------------------ inference driver pieces
+
+@pytest.mark.parametrize('num,kind,bounds,mode', [(4096, 'greater', 5.0, 4), (524288, 'greater', 5.0, 4),
+                                                  (4096, 'carla', 16.0, 4), (524288, 'carla', 16.0, 4),
+                                                  (100000, 'carla', 20.0, 2)])
+def test_device_grid_queries_bit_identical_to_numpy(num, kind, bounds, mode):
+    from o4d import geometry
+    want = geometry.sample_implicit_points_blind_numpy(num, -1.0, bounds, 3, kind, mode, 'grid')
+    got = geometry.sample_implicit_points_blind_device(num, -1.0, bounds, 3, kind, mode, DEV)
+    assert tuple(got.shape) == want.shape
+    assert torch.equal(got.cpu(), torch.from_numpy(want))
+
+
+def test_output_activation_matches_inference_loop():
+    from o4d import geometry
+    g = torch.Generator().manual_seed(4)
+    for d_out, kw in ((9, dict(color_mode='rgb', track_mode='yes')),
+                      (33, dict(color_mode='hsv', predict_segmentation=True, semantic_classes=13, track_mode='yes',
+                                output_track_idx=15)),
+                      (5, dict(color_mode='rgb_nosigmoid'))):
+        x = torch.randn(1000, d_out, generator=g) * 4
+        ops_ = geometry.inference_column_ops(d_out, **kw)
+        want = x.clone()
+        for c, op in enumerate(ops_):
+            if op == geometry.SIGMOID:
+                want[:, c] = torch.sigmoid(x[:, c])
+            elif op == geometry.CLAMP01:
+                want[:, c] = torch.clamp(x[:, c], 0.0, 1.0)
+        got = geometry.output_activation(x.to(DEV), ops_).cpu()
+        assert float((got - want).abs().max()) < 1e-6
+        keep = [c for c, op in enumerate(ops_) if op == geometry.KEEP]
+        assert torch.equal(got[:, keep], x[:, keep])

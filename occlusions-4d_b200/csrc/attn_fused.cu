@@ -13,15 +13,19 @@
 // (n, k, 2d) intermediates live in TMEM / shared memory only.
 //
 // The hidden layer is walked in chunks of 32 units.  For chunk c the tensor core computes
-// acc1 = r Wc[c]^T (128 x 32, TMEM), the four row warps pull it into registers, add the
-// gathered Qa_i - Ka_j slice, apply ReLU, split to bf16 hi/lo and store it as the next
-// A operand; MMA2 accumulates it against W_a2[:, c] into the (128 x d) logits accumulator.
-// acc1 and the A2 buffer are double buffered so chunk c+1's first MMA and epilogue overlap
-// chunk c's second MMA.  Weights arrive as pre-packed shared-memory images through
-// cp.async.bulk (two 56 KB stages).  All contractions use the bf16x3 split (hi*hi + lo*hi +
-// hi*lo, fp32 accumulate) unless `split` is 0.
+// acc1 = r Wc[c]^T (128 x 32 fp32, TMEM); the eight row warps pull it into registers, add the
+// staged Qa_i - Ka_j slice, apply ReLU, split to bf16 hi/lo and write the result back into
+// the SAME tensor-memory columns, where MMA2 reads it as its A operand (tcgen05.mma with A in
+// TMEM) and accumulates it against W_a2[:, c] into the (128 x d) logits accumulator.  The acc1 /
+// hidden buffers form a ring of three.  Weights arrive as pre-packed shared-memory images
+// through cp.async.bulk (two 53 KB W_a2 stages + a ring of four 4 KB Wc stages); the Qa / Ka / V
+// slices through cooperative cp.async into two gather stages.  All contractions use the bf16x3
+// split (hi*hi + lo*hi + hi*lo, fp32 accumulate) unless `split` is 0.
 //
-// TMEM: columns [0, d) logits, [448, 512) the two acc1 buffers.  One CTA per SM.
+// Warps: 0-7 row warps (TMEM lane quarter w & 3, column half w >> 2), 8 weight stream (and ninth
+// reduce warp of the softmax epilogue), 9 MMA2 issuer, 10 MMA1 / delta issuer.
+// TMEM: columns [0, d) logits, [416, 512) the three acc1 / hidden buffers.  One CTA per SM.
+// How the kernel got here (what bound it at each step, measured): DESIGN.md section 4.
 #include "o4d_common.cuh"
 #include <cuda_bf16.h>
 

@@ -1,15 +1,19 @@
 // 2-CTA (cta_group::2) version of the tcgen05 dense layer in gemm_tc.cu.
+// GENERATED from gemm_tc.cu by tools/gen_tc2.py (kernel body and helpers; this header and the host
+// launchers at the bottom are kept): edit gemm_tc.cu / the generator, not the kernel here.
 //
-// Measured in round 1: the dense layer is bound by bytes entering the SM
-// (~30 B/cycle/SM), of which 62 % are weights every CTA re-streams for its 128 rows.  Here two
-// CTAs of a cluster (two SMs of one TPC) form a pair: each loads its own 128 rows of A but only
+// Two CTAs of a cluster (two SMs of one TPC) form a pair: each loads its own 128 rows of A but only
 // HALF of the weight tile's rows; the leader CTA issues tcgen05.mma.cta_group::2 (M = 256:
 // rows 0-127 accumulate in the leader's TMEM, rows 128-255 in the peer's, B read half from each
-// CTA's shared memory), so weight ingest per SM halves (42.6 -> 29.3 KB per 32-wide K chunk).
+// CTA's shared memory), so weight bytes per SM halve (42.6 -> 29.3 KB per 32-wide K chunk).
 //   full[s]  (leader) : 8 local producer arrivals + 1 local weight copy + 8 remote producer arrivals;
 //                       the peer's warp 0 first waits for the peer's own weight half (peer-local full[s])
 //   empty[s], accum   : tcgen05.commit ... multicast::cluster -> the barrier at the same offset in both CTAs
 // Everything else (producers, epilogue, bf16x3 split) is the 1-CTA kernel's.
+// Status (round 1): parity green on every dense-layer test (O4D_TC_PAIR=1), but slower than the 1-CTA
+// kernel (dense family 30.0 vs 25.0 ms per step): the dense layer is bound by its A loads, not by weight
+// bytes, and the cross-CTA arrivals add latency.  Kept as the working template of
+// the pair protocol (cluster launch, cta_group::2 alloc / mma / multicast commit, remote mbarrier arrive).
 #include "o4d_common.cuh"
 #include <cuda_bf16.h>
 

@@ -164,3 +164,50 @@ def test_shard_ranges_cover_exactly():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_grid_query_count_matches_numpy_sampler():
+    """o4d_grid_query_count is host-only arithmetic (utils/geometry.py:1248-1250): same lattice as the numpy mirror."""
+    import ctypes
+    import numpy as np
+    from o4d import geometry
+    L = _lib.lib()
+    for num, kind, bounds, mode in ((4096, 'greater', 5.0, 4), (524288, 'greater', 5.0, 4), (2097152, 'greater', 5.0, 4),
+                                    (4096, 'carla', 16.0, 4), (524288, 'carla', 16.0, 4), (2097152, 'carla', 16.0, 4),
+                                    (100000, 'carla', 20.0, 1), (77, 'carla', 20.0, 2), (1000, 'carla', 20.0, 3)):
+        (x0, x1), (y0, y1), (z0, z1) = geometry.cuboid_bounds(-1.0, bounds, kind, mode)
+        ext = (ctypes.c_double * 3)(x1 - x0, y1 - y0, z1 - z0)
+        counts = (ctypes.c_int32 * 3)()
+        total = L.o4d_grid_query_count(num, ext, counts)
+        want = geometry.sample_implicit_points_blind_numpy(num, -1.0, bounds, 0, kind, mode, 'grid')
+        assert total == want.shape[0] >= num
+        per_axis = [len(np.unique(want[:, a])) for a in range(3)]
+        assert list(counts) == per_axis
+    assert L.o4d_grid_query_count(0, ext, counts) == -1
+
+
+def test_inference_column_ops_follow_the_reference_loop():
+    """eval/inference.py:218-243: which output columns get a sigmoid / clamp."""
+    from o4d import geometry as G
+    assert G.inference_column_ops(5) == [G.SIGMOID] * 4 + [G.KEEP]
+    assert G.inference_column_ops(5, track_mode='yes') == [G.SIGMOID] * 5
+    ops = G.inference_column_ops(33, color_mode='hsv', predict_segmentation=True, semantic_classes=13,
+                                 track_mode='yes', output_track_idx=15)
+    assert ops[0] == G.SIGMOID and ops[1:13] == [G.SIGMOID] * 12 and ops[13:15] == [G.CLAMP01] * 2
+    assert ops[15] == G.SIGMOID and ops[20:] == [G.SIGMOID] * 13 and ops[16:20] == [G.KEEP] * 4
+    assert G.inference_column_ops(10, color_mode='bins') == [G.SIGMOID] * 10
+
+
+def test_grad_mode_routes_to_the_training_path():
+    """With grad enabled the modules must take o4d/autograd.py (and still refuse CPU tensors); under
+    no_grad they take the fused inference path."""
+    from o4d.point_transformer_layer import _wants_grad
+    enc, dec = configs.build_modules(configs.TINY_GREATER)
+    x = torch.zeros(4, 8)
+    assert _wants_grad(enc, x)
+    with torch.no_grad():
+        assert not _wants_grad(enc, x)
+    for p in dec.parameters():
+        p.requires_grad_(False)
+    assert not _wants_grad(dec, x)
+    assert _wants_grad(dec, x.clone().requires_grad_(True))

@@ -441,6 +441,21 @@ int tc2_pack_launch(const float* W, int64_t n, int64_t k, int64_t ldw, void* pac
 int linear_tc2_packed_launch(const float* A, int64_t rows, int64_t k, int64_t lda, const void* packed, int64_t n,
                              const float* bias, const float* R, int64_t ldr, float* C, int64_t ldc, int flags,
                              int precision, cudaStream_t st, const RowGather* gp);
+// Persistent warp-specialized variant, gemm_tcp.cu (same packed-weight format).  Opt-in (O4D_TC_PERSIST=1):
+// parity green, but measured slower than this kernel (dense family 27.8 vs 22.0 ms per step, see gemm_tcp.cu).
+int linear_tcp_packed_launch(const float* A, int64_t rows, int64_t k, int64_t lda, const void* packed, int64_t n,
+                             const float* bias, const float* R, int64_t ldr, float* C, int64_t ldc, int flags,
+                             int precision, cudaStream_t st, const RowGather* gp);
+static bool tc_persistent(int64_t rows, int64_t n, int64_t ktot) {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("O4D_TC_PERSIST");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    // worth it once every SM has at least two tiles to overlap
+    return v == 1 && cdiv(rows, tc::BM) * tc::pack_meta((int)n, (int)ktot).ntiles >= 2 * 148;
+}
+
 static bool tc_pair(int64_t n, int64_t k) {
     static int v = -1;
     if (v < 0) {
@@ -471,8 +486,11 @@ int linear_tc_packed_launch(const float* A, int64_t rows, int64_t k, int64_t lda
                             const float* bias, const float* R, int64_t ldr, float* C, int64_t ldc, int flags,
                             int precision, cudaStream_t st, const RowGather* gp) {
     if (rows == 0) return 0;
-    if (tc_pair(n, gp && gp->a2 ? cdiv(k, tc::BK) * tc::BK + gp->k2 : k))
+    const int64_t ktot_ = gp && gp->a2 ? cdiv(k, tc::BK) * tc::BK + gp->k2 : k;
+    if (tc_pair(n, ktot_))
         return linear_tc2_packed_launch(A, rows, k, lda, packed, n, bias, R, ldr, C, ldc, flags, precision, st, gp);
+    if (tc_persistent(rows, n, ktot_))
+        return linear_tcp_packed_launch(A, rows, k, lda, packed, n, bias, R, ldr, C, ldc, flags, precision, st, gp);
     RowGather g;
     if (gp) g = *gp;
     static bool attr_done = false;

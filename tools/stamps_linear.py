@@ -17,7 +17,7 @@ def run(rows,k,n,res,relu_in=False,reps=5):
     e0.record()
     for _ in range(reps): ops.linear(a,w,b,residual=r,relu_in=relu_in,precision=1,out=out)
     e1.record(); torch.cuda.synchronize()
-    buf=(ctypes.c_longlong*16)(); (h.o4d_debug_read_tc2 if __import__("os").environ.get("O4D_TC_PAIR")=="1" else h.o4d_debug_read_tc)(buf); v=list(buf)
+    buf=(ctypes.c_longlong*16)(); (h.o4d_debug_read_tc2 if os.environ.get("O4D_TC_PAIR")=="1" else h.o4d_debug_read_tc)(buf); v=list(buf)
     print('rows %6d k %4d n %4d res %d: %.1f us  loop %6d wait %5d epi %6d' % (rows,k,n,res,e0.elapsed_time(e1)/reps*1e3, v[1]-v[0], v[2]-v[1], v[3]-v[2]))
 for rows in (2048, 8192, 18944, 32768, 65536):
     run(rows,416,416,1); run(rows,416,416,0)

@@ -17,14 +17,14 @@
 // maximum.
 #include "o4d_common.cuh"
 #include <math_constants.h>
+#include <stdlib.h>
 
 namespace o4d {
 namespace fc {
 
-constexpr int CTAS = 8;
+constexpr int MAX_CTAS = 8;
 constexpr int THREADS = 512;
 constexpr int WARPS = THREADS / 32;
-constexpr int STRIDE = CTAS * THREADS;     // points are dealt out round-robin over all 4096 threads
 
 __device__ __forceinline__ float sqdist3(float ax, float ay, float az, float bx, float by, float bz) {
     float dx = ax - bx, dy = ay - by, dz = az - bz;
@@ -52,12 +52,15 @@ __device__ __forceinline__ void st_remote_u64_addr(uint32_t ra, uint64_t v) {
 }
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-template <int P>
-__global__ void __cluster_dims__(CTAS, 1, 1) __launch_bounds__(THREADS, 1)
+// CTAS = cluster size (launch attribute), P = points per thread; points are dealt out round-robin over all
+// CTAS * THREADS threads of the cluster.
+template <int CTAS, int P>
+__global__ void __launch_bounds__(THREADS, 1)
 fps_cluster_kernel(const float* __restrict__ xyz, int n, int64_t ld, int n_out, int start,
                    int32_t* __restrict__ counts,   // (n) zero-initialised
                    int64_t* __restrict__ order64) {
     extern __shared__ float s_xyz[];               // sx[n], sy[n], sz[n]
+    constexpr int STRIDE = CTAS * THREADS;
     constexpr int NCAND = CTAS;                    // one candidate per CTA of the cluster
     __shared__ float s_val[WARPS];
     __shared__ int s_idx[WARPS];
@@ -158,29 +161,61 @@ fps_cluster_kernel(const float* __restrict__ xyz, int n, int64_t ld, int n_out, 
 }  // namespace fc
 
 // Returns O4D_E_UNSUPPORTED when the cloud does not fit this kernel (the caller falls back).
+template <int CTAS, int P>
+static int fps_cluster_launch_t(const float* xyz, int64_t n, int64_t ld, int64_t n_out, int64_t start, int32_t* counts,
+                                int64_t* order64, size_t smem, cudaStream_t st) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        O4D_CUDA(cudaFuncSetAttribute(fc::fps_cluster_kernel<CTAS, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_done = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CTAS, 1, 1);
+    cfg.blockDim = dim3(fc::THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CTAS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    O4D_CUDA(cudaLaunchKernelEx(&cfg, fc::fps_cluster_kernel<CTAS, P>, xyz, (int)n, ld, (int)n_out, (int)start, counts, order64));
+    count_launch();
+    return 0;
+}
+
 int fps_cluster_launch(const float* xyz, int64_t n, int64_t ld, int64_t n_out, int64_t start, int32_t* counts,
                        int64_t* order64, cudaStream_t st) {
     const size_t smem = (size_t)3 * n * sizeof(float);
-    if (n <= 2048 || n > 5 * fc::STRIDE || smem > 200 * 1024) return O4D_E_UNSUPPORTED;
-    static bool attr_done = false;
-    if (!attr_done) {
-        O4D_CUDA(cudaFuncSetAttribute(fc::fps_cluster_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        O4D_CUDA(cudaFuncSetAttribute(fc::fps_cluster_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        O4D_CUDA(cudaFuncSetAttribute(fc::fps_cluster_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        O4D_CUDA(cudaFuncSetAttribute(fc::fps_cluster_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_done = true;
+    if (n <= 2048 || smem > 200 * 1024) return O4D_E_UNSUPPORTED;
+    static int ctas = 0;
+    if (ctas == 0) {
+        const char* e = getenv("O4D_FPS_CTAS");          // cluster size: 2, 4 or 8 (default)
+        ctas = e ? atoi(e) : 8;
+        if (ctas != 2 && ctas != 4) ctas = 8;
     }
-    const int ppt = (int)cdiv(n, fc::STRIDE);
-    if (ppt <= 1)
-        fc::fps_cluster_kernel<1><<<fc::CTAS, fc::THREADS, smem, st>>>(xyz, (int)n, ld, (int)n_out, (int)start, counts, order64);
-    else if (ppt <= 2)
-        fc::fps_cluster_kernel<2><<<fc::CTAS, fc::THREADS, smem, st>>>(xyz, (int)n, ld, (int)n_out, (int)start, counts, order64);
-    else if (ppt <= 4)
-        fc::fps_cluster_kernel<4><<<fc::CTAS, fc::THREADS, smem, st>>>(xyz, (int)n, ld, (int)n_out, (int)start, counts, order64);
-    else
-        fc::fps_cluster_kernel<5><<<fc::CTAS, fc::THREADS, smem, st>>>(xyz, (int)n, ld, (int)n_out, (int)start, counts, order64);
-    O4D_LAUNCH_CHECK();
-    return 0;
+    const int ppt = (int)cdiv(n, (int64_t)ctas * fc::THREADS);
+#define O4D_FC(C, PV) return fps_cluster_launch_t<C, PV>(xyz, n, ld, n_out, start, counts, order64, smem, st)
+    if (ctas == 8) {
+        if (ppt <= 1) O4D_FC(8, 1);
+        if (ppt <= 2) O4D_FC(8, 2);
+        if (ppt <= 4) O4D_FC(8, 4);
+        if (ppt <= 5) O4D_FC(8, 5);
+    } else if (ctas == 4) {
+        if (ppt <= 2) O4D_FC(4, 2);
+        if (ppt <= 4) O4D_FC(4, 4);
+        if (ppt <= 8) O4D_FC(4, 8);
+        if (ppt <= 9) O4D_FC(4, 9);
+    } else {
+        if (ppt <= 4) O4D_FC(2, 4);
+        if (ppt <= 8) O4D_FC(2, 8);
+        if (ppt <= 16) O4D_FC(2, 16);
+        if (ppt <= 17) O4D_FC(2, 17);
+    }
+#undef O4D_FC
+    return O4D_E_UNSUPPORTED;
 }
 
 }  // namespace o4d

@@ -327,6 +327,61 @@ int o4d_grid_queries_f32(const int32_t* counts3, const double* extent3, const do
  * col_ops_host[c] = 0 keep the logit, 1 sigmoid, 2 clamp to [0, 1]  (HOST array of g bytes). */
 int o4d_output_activation_f32(float* out, int64_t n, int g, const uint8_t* col_ops_host, void* stream);
 
+/* ================================================================== training-time query sampler pieces
+ * (GuidedImplicitPointSampler, utils/geometry.py:578-1105, called once per frame
+ * on the critical path of a training step, pipeline.py:176.)
+ *
+ * filter_air_solid_gap (utils/geometry.py:1164-1196) + select_safely (utils/geometry.py:1095-1105) in one call:
+ * every candidate row cand[i, :d] (first three columns x, y, z) whose Euclidean distance to its nearest
+ * target point is > radius is kept, in input order.
+ *   num_select == 0: boolean-mask semantics -- out[0..n') = the kept rows, dist_out[0..n') their 1-NN
+ *                    distances; out / dist_out must hold n rows.
+ *   num_select  > 0: select_safely semantics -- out[j] = kept row (j mod n') for j < num_select (the
+ *                    reference's repeated doubling); zeros when nothing was kept.  No host sync is needed.
+ *   count_out (device int32) receives n' either way.  dist_out may be NULL.
+ * Distances are fp32 sqrt((dx*dx + dy*dy) + dz*dz) without FMA contraction (torch.linalg.norm rounds the
+ * same quantity within 2 ulp).  Workspace: o4d_filter_workspace_bytes(n). */
+size_t o4d_filter_workspace_bytes(int64_t n);
+int o4d_filter_air_solid_gap_f32(const float* cand, int64_t n, int d, int64_t ldc,
+                                 const float* target, int64_t m, int64_t ldt, float radius,
+                                 int64_t num_select, float* out, int64_t ldo, float* dist_out,
+                                 int32_t* count_out, void* ws, size_t ws_bytes, void* stream);
+
+/* filter_pcl_bounds_torch (utils/geometry.py:175-188): rows with lo[c] <= pcl[i, c] <= hi[c] for c = 0..2,
+ * in input order; lo3_host / hi3_host are HOST arrays of three floats; out holds up to n rows; count_out
+ * (device int32) receives the number kept.  Workspace: o4d_filter_workspace_bytes(n). */
+int o4d_filter_bounds_f32(const float* pcl, int64_t n, int d, int64_t ld, const float* lo3_host,
+                          const float* hi3_host, float* out, int64_t ldo, int32_t* count_out,
+                          void* ws, size_t ws_bytes, void* stream);
+
+/* ================================================================== implicit loss heads
+ * (MyLosses.implicit_{density,color,segm,track}_loss, loss.py:50-198, applied to
+ * every frame's decoder output in a training step, loss.py:236-254.)
+ *
+ * output (n, g) logits, target (n, 6) = (density, R, G, B, mark_track, segm) with -1 = not available.
+ * color_mode: O4D_COLOR_RGB ('rgb' and 'rgb_nosigmoid': L1 on columns 1..3), O4D_COLOR_HSV (12-way hue CE on
+ * columns 1..12 over rows with saturation and value >= 0.2 -- only when at least 16 such rows exist --, L1 on
+ * saturation / value columns 13, 14), O4D_COLOR_BINS (9-way CE on columns 1..9); HSV targets are derived from
+ * the RGB target as utils/utils.py:169-191 does.  semantic_classes = 0 disables the segmentation head (else it
+ * reads the last semantic_classes columns), track_idx < 0 disables the tracking head.
+ * Forward: losses4_out (device, 4 floats) = (loss_rgb, loss_dens, loss_segm, loss_track), each the mean over its
+ * supervised rows (NaN when there are none, like torch); stats_out (device, O4D_LOSS_STATS doubles) keeps the
+ * sums and counts for the backward call.  Deterministic (fixed reduction order).
+ * Backward: doutput (n, g) = sum_h dlosses4[h] * d loss_h / d output (every column written; dlosses4 on device). */
+#define O4D_COLOR_RGB 0
+#define O4D_COLOR_HSV 1
+#define O4D_COLOR_BINS 2
+#define O4D_LOSS_STATS 12
+size_t o4d_implicit_loss_workspace_bytes(int64_t n);
+int o4d_implicit_loss_forward_f32(const float* output, int64_t n, int g, int64_t ldo,
+                                  const float* target, int64_t ldt, int color_mode,
+                                  int semantic_classes, int track_idx, float* losses4_out,
+                                  double* stats_out, void* ws, size_t ws_bytes, void* stream);
+int o4d_implicit_loss_backward_f32(const float* output, int64_t n, int g, int64_t ldo,
+                                   const float* target, int64_t ldt, int color_mode,
+                                   int semantic_classes, int track_idx, const double* stats,
+                                   const float* dlosses4, float* doutput, int64_t lddo, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,7 +22,6 @@
 namespace o4d {
 namespace fc {
 
-constexpr int MAX_CTAS = 8;
 constexpr int THREADS = 512;
 constexpr int WARPS = THREADS / 32;
 

@@ -168,6 +168,10 @@ int knn_launch(const float* query, int64_t nq, int64_t ldq, const float* ref, in
     if (nq * 1 < 600000 && m >= 128) S = 4;
     if (nq * 4 < 600000 && m >= 1024) S = 32;
     dim3 g;
+    if (k == 1) {  // nearest neighbour only (the sampler's air / solid gap filter): a single register pair
+        return sqrt_dist ? knn_dispatch_s<1, true>(S, g, query, nq, ldq, ref, (int)m, ldr, k, idx32, idx64, dist, st)
+                         : knn_dispatch_s<1, false>(S, g, query, nq, ldq, ref, (int)m, ldr, k, idx32, idx64, dist, st);
+    }
     if (k <= 8) {
         return sqrt_dist ? knn_dispatch_s<8, true>(S, g, query, nq, ldq, ref, (int)m, ldr, k, idx32, idx64, dist, st)
                          : knn_dispatch_s<8, false>(S, g, query, nq, ldq, ref, (int)m, ldr, k, idx32, idx64, dist, st);

@@ -91,6 +91,16 @@ SIGNATURES = {
     'o4d_grid_query_count': (c_i64, [c_i64, c_ptr, c_ptr]),
     'o4d_grid_queries_f32': (c_int, [c_ptr, c_ptr, c_ptr, ctypes.c_float, c_ptr, c_ptr]),
     'o4d_output_activation_f32': (c_int, [c_ptr, c_i64, c_int, c_ptr, c_ptr]),
+    'o4d_implicit_loss_workspace_bytes': (c_size, [c_i64]),
+    'o4d_implicit_loss_forward_f32': (c_int, [c_ptr, c_i64, c_int, c_i64, c_ptr, c_i64, c_int, c_int, c_int,
+                                              c_ptr, c_ptr, c_ptr, c_size, c_ptr]),
+    'o4d_implicit_loss_backward_f32': (c_int, [c_ptr, c_i64, c_int, c_i64, c_ptr, c_i64, c_int, c_int, c_int,
+                                               c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
+    'o4d_filter_workspace_bytes': (c_size, [c_i64]),
+    'o4d_filter_air_solid_gap_f32': (c_int, [c_ptr, c_i64, c_int, c_i64, c_ptr, c_i64, c_i64, ctypes.c_float,
+                                             c_i64, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_size, c_ptr]),
+    'o4d_filter_bounds_f32': (c_int, [c_ptr, c_i64, c_int, c_i64, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr,
+                                      c_size, c_ptr]),
 }
 
 _lib = None

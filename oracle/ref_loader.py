@@ -57,6 +57,23 @@ def load():
     return _cache
 
 
+def load_extra(name):
+    """One more flat module of the reference (e.g. 'loss'), imported from inside the reference tree."""
+    load()
+    if name in _cache:
+        return _cache[name]
+    import importlib
+    cwd = os.getcwd()
+    os.chdir(REF_ROOT)
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            _cache[name] = importlib.import_module(name)
+    finally:
+        os.chdir(cwd)
+    return _cache[name]
+
+
 def load_checkpoint(which):
     """which in {'greater','carla'} -> dict with pcl_args, implicit_args, pcl_net, implicit_net."""
     import torch

@@ -263,3 +263,41 @@ def test_fused_attention_decoder_shapes_match_oracle(d_hidden, d_local, k_cross,
     with torch.no_grad():
         out2, _ = dec(query.to(DEV), abstract.to(DEV), glob.to(DEV), None)
     assert relerr(out2.cpu(), want) < 5e-2
+
+
+# ------------------------------------------------------------ test-time driver
+
+def test_inference_frame_loop_equals_the_reference_formulation():
+    """o4d.inference.run_frame (device lattice, mini-batches into one buffer, fused squashing, one D2H) against
+    the eval/inference.py:175-248 formulation: numpy lattice, per-mini-batch upload / decode / torch sigmoid."""
+    from o4d import geometry, inference
+    cfg = configs.C1_GREATER
+    g = load('c1_greater_seeded.npz')
+    enc, dec = modules_from_golden(cfg, g)
+    pcl = g['pcl'].to(DEV)[None]
+    res = inference.run_frame(enc, dec, pcl, 4096, -1.0, 5.0, 2, 'greater', 4, point_sample_mode='grid',
+                              batch_size=1000, color_mode='rgb', density_threshold=0.5, to_host=True)
+    pts = geometry.sample_implicit_points_blind_numpy(4096, -1.0, 5.0, 2, 'greater', 4, 'grid')
+    assert res['points_query'].shape == (4332, 4) and np.array_equal(res['points_query'].cpu().numpy(), pts)
+    with torch.no_grad():
+        abstract, glob, _ = enc(pcl, False)
+        chunks = []
+        for s in range(0, pts.shape[0], 1000):
+            o = dec(torch.from_numpy(pts[s:s + 1000]).to(DEV), abstract[0], glob[0], None)[0]
+            o[..., 0] = torch.sigmoid(o[..., 0])
+            o[..., 1:4] = torch.sigmoid(o[..., 1:4])
+            chunks.append(o.cpu().numpy())
+    want = np.concatenate(chunks, axis=0)
+    assert res['implicit_output'].shape == want.shape
+    np.testing.assert_allclose(res['implicit_output'], want, rtol=0, atol=2e-6)
+    assert np.array_equal(res['points_io'][:, :4], pts)
+    assert np.array_equal(res['solid_mask'], res['implicit_output'][:, 0] >= 0.5)
+    # device-resident form, random queries (the reference's numpy draws, uploaded once)
+    np.random.seed(5)
+    q = inference.query_points(3000, -1.0, 5.0, 1, 'greater', 4, 'random', DEV)
+    np.random.seed(5)
+    assert np.array_equal(q.cpu().numpy(),
+                          geometry.sample_implicit_points_blind_numpy(3000, -1.0, 5.0, 1, 'greater', 4, 'random'))
+    dev = inference.query_frame(dec, abstract[0], glob[0], q, batch_size=4096, color_mode='rgb')
+    assert dev['implicit_output'].is_cuda and dev['points_io'].shape == (3000, 4 + cfg['implicit_args']['d_out'])
+    assert bool(((dev['implicit_output'][:, :4] >= 0) & (dev['implicit_output'][:, :4] <= 1)).all())

@@ -227,3 +227,16 @@ def test_loss_module_surface():
     assert [o4d_loss.get_track_idx(m) for m in ('rgb', 'rgb_nosigmoid', 'hsv', 'bins')] == [4, 4, 15, 10]
     with pytest.raises(RuntimeError, match='no CPU fallback'):
         o4d_loss.implicit_loss_heads(torch.zeros(4, 5), torch.zeros(4, 6))
+
+
+def test_inference_driver_has_no_cpu_path():
+    from o4d import inference
+    with pytest.raises(AssertionError, match='CUDA'):
+        inference.query_frame(None, torch.zeros(8, 291), torch.zeros(128), torch.zeros(16, 4))
+    # 'random' queries keep the reference's numpy draws
+    np.random.seed(2)
+    a = inference.query_points(50, -1.0, 5.0, 3, 'greater', 4, 'random', 'cpu')
+    np.random.seed(2)
+    from o4d import geometry as geo
+    b = geo.sample_implicit_points_blind_numpy(50, -1.0, 5.0, 3, 'greater', 4, 'random')
+    assert np.array_equal(a.numpy(), b) and a.shape == (50, 4)

@@ -116,6 +116,51 @@ def cpu_reference_rate(sample, threads=None):
     return sample / dt, dt, torch.get_num_threads()
 
 
+def torch_eager_gpu_rate(dev, dec, abstract, glob, q_dev, batch, batches=2):
+    """The north star's denominator on the SAME GPU: the reference's PyTorch eager formulation of the decoder
+    (oracle port on `dev`, fp32, TF32 off: full distance matrix + sort per kNN, materialised (N, K, D) gathers,
+    one cuBLAS SGEMM per nn.Linear) on `batches` mini-batches of the workload.  Baseline measurement only."""
+    from oracle import o4d_oracle as orc
+    from tests import configs
+    cfg = configs.C2_GREATER
+
+    def knn_on_device(query_xyz, ref_xyz, k, sqrt=False, chunk=2048):
+        idx, dist = [], []
+        for s in range(0, query_xyz.shape[0], chunk):
+            d2 = orc._pair_sqdist(query_xyz[s:s + chunk], ref_xyz)
+            if sqrt:
+                d2 = d2.sqrt()
+            val, order = torch.sort(d2, dim=1, stable=True)
+            idx.append(order[:, :k])
+            dist.append(val[:, :k])
+        return torch.cat(idx), torch.cat(dist)
+
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    saved = orc.knn_indices
+    orc.knn_indices = knn_on_device          # the oracle's own helper allocates on the CPU and uses numpy's sqrt
+    try:
+        sd = {k: v.detach().float().to(dev) for k, v in dec.state_dict().items()}
+        n = min(q_dev.shape[0], batches * batch)
+        q = q_dev[torch.linspace(0, q_dev.shape[0] - 1, n, device=q_dev.device).long()]
+        with torch.no_grad():
+            ref_out = orc.decoder_forward(sd, cfg['implicit_args'], q, abstract, glob, chunk=batch)[0]   # warm-up
+            if dev.type == 'cuda':
+                torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            orc.decoder_forward(sd, cfg['implicit_args'], q, abstract, glob, chunk=batch)
+            if dev.type == 'cuda':
+                torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        return {'value': n / dt, 'unit': UNIT, 'kind': 'port', 'seconds': dt, 'tf32': False,
+                'sample': '%d of %d grid queries (evenly strided) in mini-batches of %d, decoder only, oracle port '
+                          'as torch eager fp32 on the same GPU' % (n, q_dev.shape[0], batch)}, q, ref_out
+    finally:
+        orc.knn_indices = saved
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+
+
 def run_reference(args):
     """CPU arm: the reference's algorithm (oracle port; the reference is Python and cannot travel
     to the GPU box) on the host cores, each step a bounded sample of the same workload."""
@@ -160,6 +205,58 @@ def run_reference(args):
             'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line))
+
+
+def sampler_and_loss_timing(dev):
+    """SURVEY.md 8f rows 1 and 3 at the config-5 shape, timed on their own (the sampler is excluded from the
+    train-step timing): GuidedImplicitPointSampler on 28,672-point CARLA target frames
+    (7,168 solid + 10,035 air queries per frame) and the fused loss heads on 17,203 x 18 logits."""
+    try:
+        import logging
+        from o4d import geometry as geo, loss as o4d_loss
+        g = torch.Generator().manual_seed(1830)
+        lo, hi = torch.tensor([0.0, -16.0, -1.0]), torch.tensor([40.0, 16.0, 6.4])
+        frames = []
+        for _ in range(4):
+            f = torch.rand(1, 28672, 11, generator=g)
+            f[0, :, :3] = f[0, :, :3] * (hi - lo) + lo
+            f[0, :, 5] = torch.randint(0, 13, (28672,), generator=g).float()
+            frames.append(f.to(dev))
+        sizes = [torch.tensor([28672]) for _ in range(4)]
+        valo, num_valo = torch.zeros(1, 4), torch.zeros(1, dtype=torch.int64)
+        smp = geo.GuidedImplicitPointSampler(
+            logging.getLogger('bench'), min_z=-1.0, cube_bounds=16.0, point_occupancy_radius=0.2, num_solid=7168,
+            num_air=10035, predict_segmentation=True, semantic_classes=13, data_kind='carla',
+            point_sample_bias='none', cube_mode=4, device_rng=True)
+
+        def timed(fn, iters):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / iters
+
+        sampler_ms = timed(lambda: smp(frames, sizes, valo, num_valo, 1), 10)
+        solid_in, air_in, solid_tgt, air_tgt, _, _ = smp(frames, sizes, valo, num_valo, 1)
+        target = torch.cat([solid_tgt[0], air_tgt[0]], dim=0)
+        out = torch.randn(target.shape[0], 18, generator=g).to(dev).requires_grad_(True)
+        w = torch.ones(4, device=dev)
+
+        def heads():
+            out.grad = None
+            (o4d_loss.implicit_loss_heads(out, target, 'rgb', 13, True) * w).sum().backward()
+
+        return {'sampler_ms_per_frame': sampler_ms, 'loss_heads_fwd_bwd_ms_per_frame': timed(heads, 20),
+                'queries_per_frame': int(target.shape[0]), 'target_points_per_frame': 28672,
+                'what': 'GuidedImplicitPointSampler (bias none, GPU generator) and fused loss heads (rgb + density + '
+                        '13-class segmentation + tracking), timed on their own; not part of ms_per_step'}
+    except Exception as exc:                   # noqa: BLE001 -- a side measurement must not take the bench line down
+        return {'error': '%s: %s' % (type(exc).__name__, exc)}
 
 
 def train_step_bench(dev, world, rank, steps):
@@ -223,7 +320,8 @@ def train_step_bench(dev, world, rank, steps):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     del opt
-    return {'ms_per_step': ms, 'samples_per_step': world, 'queries_per_sample': frames * per_frame,
+    extras = sampler_and_loss_timing(dev) if rank == 0 else None
+    return {'sampler_and_loss_heads': extras, 'ms_per_step': ms, 'samples_per_step': world, 'queries_per_sample': frames * per_frame,
             'points_per_sample': cfg['n_points'], 'query_grads_per_s': world * frames * per_frame / (ms / 1e3),
             'loss': float(total.detach()) / frames, 'steps': steps, 'precision': 'bf16x3 (fp32-grade) forward and backward',
             'what': 'CARLA config 5 shape: encoder + 4 decoder frames forward/backward, grad all-reduce, AdamW; '
@@ -377,6 +475,18 @@ def run_o4d(args):
         cpu_base = {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'port',
                     'sample': '%d of %d grid queries (evenly strided), decoder only, oracle port torch-CPU fp32, '
                               '%.1f s' % (args.cpu_sample, nq, secs)}
+    torch_gpu = None
+    if rank == 0 and world == 1 and not args.no_torch_gpu_baseline:
+        try:                                   # a reported baseline: never allowed to take the bench line down
+            with torch.no_grad():
+                torch_gpu, q_s, ref_s = torch_eager_gpu_rate(dev, dec, abstract, glob, q_dev, batch)
+                ours = torch.cat([ops.decoder_forward(dcfg, dparams, scene, q_s[s:s + batch], want_penult=False)[0]
+                                  for s in range(0, q_s.shape[0], batch)])
+            torch_gpu['o4d_over_torch_eager'] = value / torch_gpu['value']
+            torch_gpu['max_rel_err_vs_torch_eager'] = float((ours - ref_s).abs().max() / ref_s.abs().max())
+            del q_s, ref_s, ours
+        except Exception as exc:               # noqa: BLE001
+            torch_gpu = {'error': '%s: %s' % (type(exc).__name__, exc)}
     if rank == 0:
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
@@ -386,7 +496,7 @@ def run_o4d(args):
                         'd2h_bytes_per_step': nq * d_out * 4, 'steps': e2e_steps,
                         'bit_identical_to_device_path': e2e_matches},
                 'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'kernel_families': families,
-                'cpu_baseline': cpu_base,
+                'cpu_baseline': cpu_base, 'torch_gpu_baseline': torch_gpu,
                 'encoder': {'pts_per_s': cfg['n_points'] / (enc_ms / 1e3), 'ms': enc_ms, 'n_points': cfg['n_points']},
                 'train_step': train, 'tcgen05': bool(lib.o4d_has_tcgen05())}
         print(json.dumps(line))
@@ -405,6 +515,8 @@ def main():
     ap.add_argument('--cpu-sample', type=int, default=196608)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-train-step', action='store_true', help='skip the config-5 training-step timing')
+    ap.add_argument('--no-torch-gpu-baseline', action='store_true',
+                    help='skip the PyTorch-eager timing of the same decoder on the same GPU')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -240,3 +240,30 @@ def test_inference_driver_has_no_cpu_path():
     from o4d import geometry as geo
     b = geo.sample_implicit_points_blind_numpy(50, -1.0, 5.0, 3, 'greater', 4, 'random')
     assert np.array_equal(a.numpy(), b) and a.shape == (50, 4)
+
+
+@pytest.mark.reference
+def test_compat_geometry_shim_keeps_reference_names_and_overrides_the_sampler_path():
+    """compat/geometry.py first on sys.path: the reference's own helpers stay importable, the sampler path is o4d's."""
+    code = r'''
+import importlib, os, sys, warnings
+warnings.simplefilter('ignore')
+repo, ref = sys.argv[1], sys.argv[2]
+sys.path.insert(0, repo)
+sys.path.insert(0, os.path.join(repo, 'oracle', 'ref_stubs'))
+os.chdir(ref)
+sys.path.insert(0, ref)
+sys.path.insert(0, os.path.join(repo, 'occlusions-4d_b200', 'compat'))
+importlib.import_module('__init__')
+import geometry, torch
+assert geometry.__file__.endswith(os.path.join('compat', 'geometry.py'))
+assert geometry.GuidedImplicitPointSampler.__module__ == 'o4d.geometry'
+assert geometry.filter_air_solid_gap.__module__ == 'o4d.geometry'
+assert geometry.point_cloud_from_rgbd.__module__ == '_reference_geometry'
+assert geometry.subsample_pad_pcl_torch(torch.rand(10, 4), 12).shape == (12, 4)      # CPU cloud: reference path
+assert geometry.filter_pcl_bounds_torch(torch.rand(10, 4)).shape == (10, 4)
+import loss
+print('ok')
+'''
+    out = subprocess.run([os.sys.executable, '-c', code, REPO, ref_loader.REF_ROOT], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip().endswith('ok'), out.stderr[-2000:]

@@ -152,16 +152,12 @@ int knn_launch(const float* query, int64_t nq, int64_t ldq, const float* ref, in
                cudaStream_t st) {
     O4D_REQUIRE(nq >= 0, "knn: negative query count");
     O4D_REQUIRE(k >= 1 && k <= O4D_MAX_K, "knn: k=%d outside [1,%d]", k, O4D_MAX_K);
-    O4D_REQUIRE(m >= k, "knn: need k <= m (m=%lld, k=%d)", (long long)m, k);
+    O4D_REQUIRE(m >= k && m < (int64_t)0x7fffffff, "knn: need k <= m < 2^31 (m=%lld, k=%d)",
+                (long long)m, k);
     if (nq == 0) return 0;
     O4D_REQUIRE(query && ref, "knn: null input");
     O4D_REQUIRE(idx32 || idx64 || dist, "knn: no output requested");
     O4D_REQUIRE(ldq >= 3 && ldr >= 3, "knn: leading dimensions must be >= 3");
-    O4D_REQUIRE(k >= 1 && k <= O4D_MAX_K, "knn: k=%d outside [1,%d]", k, O4D_MAX_K);
-    O4D_REQUIRE(m >= k && m < (int64_t)0x7fffffff, "knn: need k <= m < 2^31 (m=%lld, k=%d)",
-                (long long)m, k);
-    O4D_REQUIRE(nq >= 0, "knn: negative query count");
-    if (nq == 0) return 0;
     ProfScope prof(PROF_KNN, 8.0 * (double)nq * (double)m, st);
     // enough threads to cover the machine (148 SMs x 2048 resident threads) a few times.
     int S = 1;

@@ -4,7 +4,6 @@
 per-frame heads are ONE fused device call (`implicit_loss_heads`: o4d_implicit_loss_forward_f32, gradients by
 o4d_implicit_loss_backward_f32) instead of ~80 small kernels and a host sync per boolean mask.  CUDA only.
 """
-import ctypes
 
 import torch
 
@@ -37,13 +36,13 @@ class _ImplicitLossHeads(torch.autograd.Function):
                 int(track_idx), ops._ptr(losses), ops._ptr(stats), ops._ptr(ws), ws.numel(), ops._stream(out2))
         _lib.check(rc, 'o4d_implicit_loss_forward_f32')
         ctx.save_for_backward(out2, tgt2, stats)
-        ctx.meta = (ldo, ldt, int(color_mode), int(semantic_classes), int(track_idx), output.shape)
+        ctx.meta = (ldo, ldt, int(color_mode), int(semantic_classes), int(track_idx), output.shape, output.dtype)
         return losses
 
     @staticmethod
     def backward(ctx, dlosses):
         out2, tgt2, stats = ctx.saved_tensors
-        ldo, ldt, color_mode, semantic_classes, track_idx, shape = ctx.meta
+        ldo, ldt, color_mode, semantic_classes, track_idx, shape, dtype = ctx.meta
         n, g = out2.shape
         w = dlosses.detach().float().contiguous()
         with torch.cuda.device(out2.device):
@@ -52,7 +51,7 @@ class _ImplicitLossHeads(torch.autograd.Function):
                 ops._ptr(out2), n, g, ldo, ops._ptr(tgt2), ldt, color_mode, semantic_classes, track_idx,
                 ops._ptr(stats), ops._ptr(w), ops._ptr(dout), g, ops._stream(out2))
         _lib.check(rc, 'o4d_implicit_loss_backward_f32')
-        return dout.reshape(shape), None, None, None, None
+        return dout.reshape(shape).to(dtype), None, None, None, None
 
 
 def implicit_loss_heads(implicit_output, implicit_target, color_mode='rgb', semantic_classes=0, track=True):

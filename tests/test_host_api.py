@@ -211,3 +211,24 @@ def test_grad_mode_routes_to_the_training_path():
         p.requires_grad_(False)
     assert not _wants_grad(dec, x)
     assert _wants_grad(dec, x.clone().requires_grad_(True))
+
+
+def test_header_is_plain_c99_and_links_from_c(tmp_path):
+    """include/o4d.h is the drop-in boundary: a C99 translation unit includes it (-pedantic, no C++ / torch
+    types), takes the address of every declared entry point, links against libo4d.so and runs (no GPU work)."""
+    import subprocess
+    names = header_symbols()
+    src = tmp_path / 'abi.c'
+    src.write_text('#include "o4d.h"\n#include <stdio.h>\ntypedef void (*fn)(void);\n'
+                   'static fn table[] = {%s};\n' % ', '.join('(fn)%s' % n for n in names) +
+                   'int main(void) {\n  unsigned i, ok = 0;\n'
+                   '  for (i = 0; i < sizeof(table) / sizeof(table[0]); ++i) ok += table[i] != 0;\n'
+                   '  printf("%u %d %d\\n", ok, o4d_abi_version(), (int)sizeof(o4d_decoder_config));\n'
+                   '  return o4d_abi_version() == 2 ? 0 : 1;\n}\n')
+    exe = tmp_path / 'abi'
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(['gcc', '-std=c99', '-Wall', '-Wextra', '-pedantic', '-Werror', '-I', os.path.join(REPO, 'include'),
+                    str(src), '-o', str(exe), '-L', libdir, '-lo4d', '-Wl,-rpath,' + libdir], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    assert int(out[0]) == len(names) and int(out[1]) == 2
+    assert int(out[2]) == ctypes.sizeof(_lib.DecoderConfig)

@@ -41,7 +41,10 @@ if _ref is not None:
     _ref_bounds = _ref.filter_pcl_bounds_torch
 
     def subsample_pad_pcl_torch(pcl, *args, **kwargs):
-        """CUDA clouds take the o4d path (cluster FPS kernel); CPU clouds (dataloader workers) the reference's."""
+        """CUDA clouds take the o4d path (cluster FPS kernel).  CPU clouds are the dataset pipeline's calls from
+        dataloader workers (data_greater.py:477, data_carla.py:538): that pipeline is out of scope and keeps running
+        the reference's own function unchanged -- this is not a CPU fallback of an o4d op
+        (o4d.geometry.subsample_pad_pcl_torch itself raises on a CPU cloud in farthest_point mode)."""
         fn = _o4d_geometry.subsample_pad_pcl_torch if pcl.is_cuda else _ref_subsample
         return fn(pcl, *args, **kwargs)
 

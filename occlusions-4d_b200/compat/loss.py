@@ -1,4 +1,4 @@
-"""Flat-name shim for the reference's ``loss.py`` (``import loss`` in pipeline.py:10).  The reference's loss.py
+"""Flat-name shim for the reference's ``loss.py`` (``import loss`` in pipeline.py:13).  The reference's loss.py
 sits next to its entry scripts, i.e. in sys.path[0], so this shim is picked up only when the reference runs as
 ``python -m`` / from another directory; otherwise bind it with one line: ``import o4d.loss as loss``
 (INTEGRATION.md)."""

@@ -355,8 +355,8 @@ int o4d_filter_bounds_f32(const float* pcl, int64_t n, int d, int64_t ld, const 
                           void* ws, size_t ws_bytes, void* stream);
 
 /* ================================================================== implicit loss heads
- * (MyLosses.implicit_{density,color,segm,track}_loss, loss.py:50-198, applied to
- * every frame's decoder output in a training step, loss.py:236-254.)
+ * (MyLosses.implicit_{density,color,segm,track}_loss, loss.py:50-194, applied to
+ * every frame's decoder output in a training step, loss.py:226-246.)
  *
  * output (n, g) logits, target (n, 6) = (density, R, G, B, mark_track, segm) with -1 = not available.
  * color_mode: O4D_COLOR_RGB ('rgb' and 'rgb_nosigmoid': L1 on columns 1..3), O4D_COLOR_HSV (12-way hue CE on

@@ -1,10 +1,10 @@
 // Implicit loss heads fused over one frame's decoder output.
 //
-// Replaces  MyLosses.implicit_density_loss  loss.py:50-63    BCE-with-logits on column 0, mean over all rows
-//           MyLosses.implicit_color_loss    loss.py:65-158   L1 on RGB | hue CE + sat / val L1 | 9-bin CE, over
+// Replaces  MyLosses.implicit_density_loss  loss.py:50-64    BCE-with-logits on column 0, mean over all rows
+//           MyLosses.implicit_color_loss    loss.py:66-154   L1 on RGB | hue CE + sat / val L1 | 9-bin CE, over
 //                                                            solid rows whose colour is available
-//           MyLosses.implicit_segm_loss     loss.py:160-178  CE on the last semantic_classes columns, rows with tag >= 0
-//           MyLosses.implicit_track_loss    loss.py:180-198  BCE-with-logits on the track column, solid rows with a label
+//           MyLosses.implicit_segm_loss     loss.py:156-173  CE on the last semantic_classes columns, rows with tag >= 0
+//           MyLosses.implicit_track_loss    loss.py:175-194  BCE-with-logits on the track column, solid rows with a label
 //           utils.rgb_to_hsv                utils/utils.py:169-191
 //
 // The reference runs ~20 small kernels per head (masks, boolean-mask indexing with a host sync each, HSV

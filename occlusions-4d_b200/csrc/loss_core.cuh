@@ -1,7 +1,7 @@
 // Per-row arithmetic of the implicit loss heads (loss.cu), written so that the SAME source also compiles for
 // the host: tests/test_host_core.py builds it with g++ (-ffp-contract=off) and checks it against the reference's
 // golden losses and gradients on CPU, so the kernel arithmetic is verified without a GPU.  Reference lines:
-// loss.py:50-198, utils/utils.py:169-191.
+// loss.py:50-194, utils/utils.py:169-191.
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -170,7 +170,7 @@ O4D_HD void finalize_losses(const Head& hd, const double* st, float* losses4) {
     if (hd.color_mode == O4D_COLOR_RGB) {
         rgb = mean_or_nan(st[S_L1A], 3.0 * st[S_COLOR_N]);
     } else if (hd.color_mode == O4D_COLOR_HSV) {
-        const double hue = st[S_CE_N] >= 16.0 ? st[S_CE] / st[S_CE_N] / 2.0 : 0.0;   // loss.py:108-114
+        const double hue = st[S_CE_N] >= 16.0 ? st[S_CE] / st[S_CE_N] / 2.0 : 0.0;   // loss.py:105-111
         rgb = (hue + mean_or_nan(st[S_L1A], st[S_COLOR_N]) + mean_or_nan(st[S_L1B], st[S_COLOR_N])) / 3.0;
     } else {
         rgb = mean_or_nan(st[S_CE], st[S_CE_N]) / 3.0;

@@ -349,7 +349,7 @@ class GuidedImplicitPointSampler(torch.nn.Module):
         return (4 if carla else 3), (5 if carla else 3), (6 if carla else 4)   # instance, semantic, view
 
     def _frame_cloud(self, frame, sizes, i, what):
-        """Valid rows of batch item i, cropped to the output cuboid for CARLA (:679-697)."""
+        """Valid rows of batch item i, cropped to the output cuboid for CARLA (:670-689)."""
         cloud = frame[i, :int(sizes[i].item())]
         if self.data_kind == 'carla':
             cloud = filter_pcl_bounds_carla_output_torch(
@@ -377,7 +377,7 @@ class GuidedImplicitPointSampler(torch.nn.Module):
             cloud = self._frame_cloud(frame, sizes, i, 'cur_tgt_pcl_count')
             ids = sorted(list(valo_ids[i, :int(num_valo_ids[i].item())].detach().cpu().numpy()))
             tgt_unique = other_unique = None
-            if 'moving' in self.point_sample_bias:               # :705-735
+            if 'moving' in self.point_sample_bias:               # :697-735
                 other = self._frame_cloud(other_frame, other_sizes, i, 'cur_other_pcl_count')
                 max_slice = int((2 ** 27) // self.num_air)
                 head = cloud.shape[0] // int(np.ceil(cloud.shape[0] / max_slice)) + 1
@@ -448,7 +448,7 @@ class GuidedImplicitPointSampler(torch.nn.Module):
             if counts[slot] > 0:
                 picked.append(self._pick(pools[slot], counts[slot]))
         want_sembal = int(shares[5] * self.num_solid)
-        if want_sembal > 0:                                      # :888-907
+        if want_sembal > 0:                                      # :884-903
             tags = cur_tgt_pcl[..., segm_idx]
             present = list(tags.type(torch.int32).unique().detach().cpu().numpy())
             for tag in present:

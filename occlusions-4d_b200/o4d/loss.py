@@ -1,6 +1,6 @@
 """Objective functions of the implicit heads (host-side mirror of the reference's loss.py).
 
-`MyLosses` keeps the reference's constructor, `per_example` and `entire_batch` (loss.py:14-294); the four
+`MyLosses` keeps the reference's constructor, `per_example` and `entire_batch` (loss.py:15-294); the four
 per-frame heads are ONE fused device call (`implicit_loss_heads`: o4d_implicit_loss_forward_f32, gradients by
 o4d_implicit_loss_backward_f32) instead of ~80 small kernels and a host sync per boolean mask.  CUDA only.
 """
@@ -18,7 +18,7 @@ def get_track_idx(color_mode):
 
 
 class _ImplicitLossHeads(torch.autograd.Function):
-    """(output (n, g), target (n, 6)) -> losses (4,) = (rgb, dens, segm, track); loss.py:50-198."""
+    """(output (n, g), target (n, 6)) -> losses (4,) = (rgb, dens, segm, track); loss.py:50-194."""
 
     @staticmethod
     def forward(ctx, output, target, color_mode, semantic_classes, track_idx):
@@ -67,7 +67,7 @@ def implicit_loss_heads(implicit_output, implicit_target, color_mode='rgb', sema
 
 
 class MyLosses():
-    """Same constructor and methods as the reference's MyLosses (loss.py:14-294)."""
+    """Same constructor and methods as the reference's MyLosses (loss.py:15-294)."""
 
     def __init__(self, stage, logger, mixed_precision, color_lw, density_lw, segmentation_lw,
                  tracking_lw, color_mode, semantic_classes, past_frames, future_frames):
@@ -101,7 +101,7 @@ class MyLosses():
         return self._heads(implicit_output, implicit_target, segm=False, track=True)[3]
 
     def per_example(self, pcl_target, pcl_target_size, implicit_output, implicit_target):
-        """loss.py:200-258: per (example, frame) heads averaged within this GPU -> (loss_rgb, loss_dens,
+        """loss.py:196-253: per (example, frame) heads averaged within this GPU -> (loss_rgb, loss_dens,
         loss_segm, loss_track), None for heads whose weight is zero.  One fused call per (example, frame)."""
         (B, M, E) = pcl_target[0].shape
         assert torch.all(torch.as_tensor(pcl_target_size) <= M)
@@ -119,7 +119,7 @@ class MyLosses():
 
     def entire_batch(self, total_step, loss_rgb, loss_dens, loss_segm, loss_track, points_query,
                      implicit_output, features_global):
-        """loss.py:260-294: average over GPUs, weight, report."""
+        """loss.py:255-294: average over GPUs, weight, report."""
         loss_rgb = loss_rgb.mean() if torch.is_tensor(loss_rgb) else 0.0
         loss_dens = loss_dens.mean() if torch.is_tensor(loss_dens) else 0.0
         loss_segm = loss_segm.mean() if torch.is_tensor(loss_segm) else 0.0

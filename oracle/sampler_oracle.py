@@ -46,7 +46,7 @@ def select_safely(rows, num_select):
 
 def filter_select(to_filter, target_coords, point_occupancy_radius, num_select):
     """filter_air_solid_gap + select_safely on rows and distances, as the sampler uses them
-    (utils/geometry.py:1009-1013, 1030-1033, 1049-1052, 1068-1071) -> (rows, dists, count (1,) int32)."""
+    (utils/geometry.py:998-1002, 1022-1025, 1044-1047, 1065-1068) -> (rows, dists, count (1,) int32)."""
     rows, dist, _ = filter_air_solid_gap(to_filter, target_coords, 0, point_occupancy_radius)
     count = torch.tensor([rows.shape[0]], dtype=torch.int32)
     if rows.shape[0] == 0:
@@ -107,7 +107,7 @@ def implicit_losses(output, target, color_mode='rgb', semantic_classes=0):
             vivid = torch.logical_and(sat >= 0.2, val >= 0.2)
             loss_hue = F.cross_entropy(o[..., 1:1 + nc][vivid], hue[vivid]) / 2.0 if vivid.sum() >= 16 else 0.0
             res['rgb'] = (loss_hue + F.l1_loss(o[..., 1 + nc], sat) + F.l1_loss(o[..., 2 + nc], val)) / 3.0
-        else:                                                                               # loss.py:118-153
+        else:                                                                               # loss.py:117-149
             nc = 6
             cls = torch.round(hsv[..., 0] / 360.0 * nc).type(torch.int64)
             cls[cls == nc] = 0
@@ -116,11 +116,11 @@ def implicit_losses(output, target, color_mode='rgb', semantic_classes=0):
             cls[torch.logical_and(torch.logical_and(0.2 <= val, val < 0.6), bland)] = nc + 1
             cls[torch.logical_and(0.6 <= val, bland)] = nc + 2
             res['rgb'] = F.cross_entropy(o[..., 1:1 + nc + 3], cls) / 3.0
-    if semantic_classes > 0:                                                                # loss.py:167-172
+    if semantic_classes > 0:                                                                # loss.py:163-168
         tag = target[..., -1].type(torch.int64)
         ok = tag >= 0
         res['segm'] = F.cross_entropy(output[..., -semantic_classes:][ok], tag[ok])
-    ti = track_idx(color_mode)                                                              # loss.py:186-196
+    ti = track_idx(color_mode)                                                              # loss.py:182-192
     if output.shape[-1] > ti:
         sel = torch.logical_and(solid, target[..., 4] >= 0.0)
         res['track'] = F.binary_cross_entropy_with_logits(output[sel][..., ti], target[sel][..., 4])

@@ -75,7 +75,7 @@ def main():
         out.grad = None
         (o4d_loss.implicit_loss_heads(out, tgt, 'rgb', 13, True) * w).sum().backward()
 
-    def eager():   # the reference's formulation (loss.py:50-198) with torch ops on the same GPU
+    def eager():   # the reference's formulation (loss.py:50-194) with torch ops on the same GPU
         out.grad = None
         F = torch.nn.functional
         o, t = out[None], tgt[None]

@@ -95,92 +95,216 @@ def golden_scene():
     return torch.from_numpy(z['abstract']), torch.from_numpy(z['glob'])
 
 
+def reference_modules(cfg, dev):
+    """The UNMODIFIED reference modules (oracle/ref_loader.py: /root/reference, or its byte-for-byte copy
+    oracle/_ref made by oracle/make_ref.py) with the config's seeded default init -- the same weights
+    configs.build_modules gives the o4d modules (same creation order, same RNG stream).  None if unavailable."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        return None
+    ref = ref_loader.load()
+    torch.manual_seed(cfg['seed'])
+    with ref_loader.quiet():
+        enc = ref['model'].PointCompletionNetV3(**cfg['pcl_args']).eval()
+        dec = ref['implicit'].LocalPclResnetFC(**cfg['implicit_args']).eval()
+    return ref_loader, enc.to(dev), dec.to(dev)
+
+
+def _median(xs):
+    return float(np.median(np.asarray(xs, dtype=np.float64)))
+
+
 def cpu_reference_rate(sample, threads=None):
-    """Oracle port (torch CPU fp32) of the decoder on `sample` queries of the workload; returns
-    (queries/s, seconds, threads)."""
-    from oracle import o4d_oracle as orc
+    """The reference decoder (implicit.LocalPclResnetFC.forward, torch CPU fp32) on `sample` evenly strided queries
+    of the workload in mini-batches of 4096; falls back to the oracle port when the reference copy is absent.
+    Returns (queries/s, seconds, threads, kind)."""
     from tests import configs
     cfg = configs.C2_GREATER
     if threads:
         torch.set_num_threads(threads)
-    _, dec = configs.build_modules(cfg)
-    sd = orc.cast_state(dec.state_dict(), torch.float32)
     abstract, glob = golden_scene()
     q = configs.synthetic_queries(cfg)
     sel = torch.linspace(0, q.shape[0] - 1, sample).long()
     q = q[sel]
+    mods = reference_modules(cfg, 'cpu')
     with torch.no_grad():
-        t0 = time.perf_counter()
-        orc.decoder_forward(sd, cfg['implicit_args'], q, abstract, glob, chunk=4096)
-        dt = time.perf_counter() - t0
-    return sample / dt, dt, torch.get_num_threads()
+        if mods is not None:
+            loader, _, dec = mods
+            with loader.quiet():
+                dec(q[:256], abstract, glob, None)                       # first-call overheads out of the timing
+                t0 = time.perf_counter()
+                for s0 in range(0, q.shape[0], 4096):
+                    dec(q[s0:s0 + 4096], abstract, glob, None)
+                dt = time.perf_counter() - t0
+            kind = 'reference'
+        else:
+            from oracle import o4d_oracle as orc
+            _, dec = configs.build_modules(cfg)
+            sd = orc.cast_state(dec.state_dict(), torch.float32)
+            t0 = time.perf_counter()
+            orc.decoder_forward(sd, cfg['implicit_args'], q, abstract, glob, chunk=4096)
+            dt = time.perf_counter() - t0
+            kind = 'port'
+    return sample / dt, dt, torch.get_num_threads(), kind
 
 
-def torch_eager_gpu_rate(dev, dec, abstract, glob, q_dev, batch, batches=2):
-    """The north star's denominator on the SAME GPU: the reference's PyTorch eager formulation of the decoder
-    (oracle port on `dev`, fp32, TF32 off: full distance matrix + sort per kNN, materialised (N, K, D) gathers,
-    one cuBLAS SGEMM per nn.Linear) on `batches` mini-batches of the workload.  Baseline measurement only."""
-    from oracle import o4d_oracle as orc
-    from tests import configs
-    cfg = configs.C2_GREATER
-
-    def knn_on_device(query_xyz, ref_xyz, k, sqrt=False, chunk=2048):
-        idx, dist = [], []
-        for s in range(0, query_xyz.shape[0], chunk):
-            d2 = orc._pair_sqdist(query_xyz[s:s + chunk], ref_xyz)
-            if sqrt:
-                d2 = d2.sqrt()
-            val, order = torch.sort(d2, dim=1, stable=True)
-            idx.append(order[:, :k])
-            dist.append(val[:, :k])
-        return torch.cat(idx), torch.cat(dist)
-
+def reference_decoder_gpu(dev, cfg, abstract, glob, q_host, batch, o4d_value, o4d_out, warm=10, iters=20):
+    """SURVEY 8d "Reference timing (1)" = the north star's denominator: implicit.LocalPclResnetFC itself, PyTorch
+    eager fp32 with TF32 off, on the SAME GPU, same weights, same scene, the eval/inference.py:204-246 loop over
+    ALL mini-batches of the frame.  10 warm-up passes, median of 20 (device-resident queries, no per-batch D2H);
+    then the loop exactly as the reference runs it (numpy slice -> .to(device) -> forward -> .cpu().numpy() per
+    mini-batch), 3 + 5 passes.  Also the largest relative difference between the reference's and o4d's outputs
+    over the whole frame."""
+    mods = reference_modules(cfg, dev)
+    if mods is None:
+        return {'error': 'reference copy (oracle/_ref) not present'}
+    loader, _, dec = mods
     tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
-    saved = orc.knn_indices
-    orc.knn_indices = knn_on_device          # the oracle's own helper allocates on the CPU and uses numpy's sqrt
     try:
-        sd = {k: v.detach().float().to(dev) for k, v in dec.state_dict().items()}
-        n = min(q_dev.shape[0], batches * batch)
-        q = q_dev[torch.linspace(0, q_dev.shape[0] - 1, n, device=q_dev.device).long()]
-        with torch.no_grad():
-            ref_out = orc.decoder_forward(sd, cfg['implicit_args'], q, abstract, glob, chunk=batch)[0]   # warm-up
-            if dev.type == 'cuda':
+        q_np = q_host.numpy()
+        q_dev = q_host.to(dev)
+        nq = q_dev.shape[0]
+
+        def pass_device():
+            return [dec(q_dev[s:s + batch], abstract, glob, None)[0] for s in range(0, nq, batch)]
+
+        def pass_host():
+            outs = []
+            for s in range(0, nq, batch):
+                qb = torch.from_numpy(q_np[s:s + batch]).to(dev)                  # inference.py:206
+                o = dec(qb, abstract, glob, None)[0]
+                o[..., 0] = torch.sigmoid(o[..., 0])                              # :218
+                outs.append(o.detach().cpu().numpy())                             # :245
+            return outs
+
+        with torch.no_grad(), loader.quiet():
+            ref_out = torch.cat(pass_device())
+            err = float((o4d_out - ref_out).abs().max() / ref_out.abs().max())
+            del ref_out
+            for _ in range(warm - 1):
+                pass_device()
+            times = []
+            for _ in range(iters):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                pass_device()
+                e1.record()
                 torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            orc.decoder_forward(sd, cfg['implicit_args'], q, abstract, glob, chunk=batch)
-            if dev.type == 'cuda':
+                times.append(e0.elapsed_time(e1))
+            host_times = []
+            for i in range(3 + 5):
                 torch.cuda.synchronize()
-            dt = time.perf_counter() - t0
-        return {'value': n / dt, 'unit': UNIT, 'kind': 'port', 'seconds': dt, 'tf32': False,
-                'sample': '%d of %d grid queries (evenly strided) in mini-batches of %d, decoder only, oracle port '
-                          'as torch eager fp32 on the same GPU' % (n, q_dev.shape[0], batch)}, q, ref_out
+                t0 = time.perf_counter()
+                pass_host()
+                torch.cuda.synchronize()
+                if i >= 3:
+                    host_times.append((time.perf_counter() - t0) * 1e3)
+        rate = nq / (_median(times) / 1e3)
+        rate_host = nq / (_median(host_times) / 1e3)
+        return {'value': rate, 'unit': UNIT, 'kind': 'reference', 'ms_per_frame': _median(times), 'tf32': False,
+                'warmup_passes': warm, 'timed_passes': iters, 'statistic': 'median',
+                'with_per_batch_h2d_d2h': {'value': rate_host, 'ms_per_frame': _median(host_times), 'timed_passes': 5},
+                'o4d_over_torch_eager': o4d_value / rate,
+                'max_rel_err_o4d_vs_reference_all_queries': err,
+                'sample': 'all %d grid queries of the frame in mini-batches of %d: the unmodified reference module '
+                          '(model/implicit.py LocalPclResnetFC, copy in oracle/_ref) as torch eager fp32 on the same '
+                          'GPU, scene encoding resident' % (nq, batch)}
     finally:
-        orc.knn_indices = saved
         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
 
 
+def reference_encoder_baselines(dev, cfg, pcl, cpu=True):
+    """Encoder pts/s of the unmodified reference module on the same GPU (torch eager fp32) and on the host cores.
+    torch_cluster is not installable: its two ops run through the CPU restatement oracle/cluster_ops.py,
+    whose time is measured separately and SUBTRACTED in `*_excl_cluster_stub` -- an upper bound on what the
+    reference with the real extension could reach."""
+    from oracle import cluster_ops
+    import torch_cluster as stub                      # the stub module ref_loader put on sys.path
+    out = {}
+    spent = [0.0]
+    saved = (stub.fps, stub.knn)
+
+    def timed(fn):
+        def wrap(*a, **k):
+            if dev != 'cpu':
+                torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            r = fn(*a, **k)
+            spent[0] += time.perf_counter() - t0
+            return r
+        return wrap
+    try:
+        for where in (['gpu_eager', 'cpu'] if cpu else ['gpu_eager']):
+            d = dev if where == 'gpu_eager' else 'cpu'
+            mods = reference_modules(cfg, d)
+            if mods is None:
+                return {'error': 'reference copy (oracle/_ref) not present'}
+            loader, enc, _ = mods
+            import modules as ref_modules            # flat module of the reference (model/modules.py)
+            ref_modules.torch_cluster.fps, ref_modules.torch_cluster.knn = timed(cluster_ops.fps), timed(cluster_ops.knn)
+            x = pcl.to(d)[None]
+            reps = 3 if where == 'gpu_eager' else 1
+            with torch.no_grad(), loader.quiet():
+                if where == 'gpu_eager':
+                    enc(x, False)
+                    torch.cuda.synchronize()
+                spent[0] = 0.0
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    enc(x, False)
+                if where == 'gpu_eager':
+                    torch.cuda.synchronize()
+                dt = (time.perf_counter() - t0) / reps
+            stub_s = spent[0] / reps
+            n = pcl.shape[0]
+            out[where] = {'pts_per_s': n / dt, 'ms': dt * 1e3, 'cluster_stub_ms': stub_s * 1e3,
+                          'pts_per_s_excl_cluster_stub': n / max(dt - stub_s, 1e-9), 'kind': 'reference',
+                          'cores': torch.get_num_threads() if where == 'cpu' else None}
+            del enc
+            if where == 'gpu_eager':
+                torch.cuda.empty_cache()
+    finally:
+        stub.fps, stub.knn = saved
+    return out
+
+
 def run_reference(args):
-    """CPU arm: the reference's algorithm (oracle port; the reference is Python and cannot travel
-    to the GPU box) on the host cores, each step a bounded sample of the same workload."""
+    """CPU arm: the reference's own decoder module (oracle/_ref copy of model/implicit.py; oracle port if the copy
+    is absent) on the host cores with all threads, each step a bounded sample of the same workload."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    from oracle import o4d_oracle as orc
     from tests import configs
     cfg = configs.C2_GREATER
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    _, dec = configs.build_modules(cfg)
-    sd = orc.cast_state(dec.state_dict(), torch.float32)
     abstract, glob = golden_scene()
     q_all = configs.synthetic_queries(cfg)
-    # calibrate on 1024 queries, then size a step so that warmup+steps take about two minutes
+    mods = reference_modules(cfg, 'cpu')
+    if mods is not None:
+        loader, _, dec = mods
+        kind = 'reference'
+
+        def forward(q):
+            with loader.quiet():
+                for s0 in range(0, q.shape[0], 4096):
+                    dec(q[s0:s0 + 4096], abstract, glob, None)
+    else:
+        from oracle import o4d_oracle as orc
+        _, dec = configs.build_modules(cfg)
+        sd = orc.cast_state(dec.state_dict(), torch.float32)
+        kind = 'port'
+
+        def forward(q):
+            orc.decoder_forward(sd, cfg['implicit_args'], q, abstract, glob, chunk=4096)
+    # calibrate on 2048 queries, then size a step so that warmup+steps take about two minutes
     with torch.no_grad():
+        forward(q_all[:1024])
         t0 = time.perf_counter()
-        orc.decoder_forward(sd, cfg['implicit_args'], q_all[:1024], abstract, glob, chunk=1024)
-        rate = 1024 / (time.perf_counter() - t0)
+        forward(q_all[:2048])
+        rate = 2048 / (time.perf_counter() - t0)
     total = args.steps + args.warmup
     sample = int(max(1024, min(q_all.shape[0], rate * 120.0 / total)))
     sample = sample // 1024 * 1024
@@ -188,23 +312,173 @@ def run_reference(args):
     q = q_all[sel]
     with torch.no_grad():
         for _ in range(args.warmup):
-            orc.decoder_forward(sd, cfg['implicit_args'], q, abstract, glob, chunk=4096)
+            forward(q)
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            orc.decoder_forward(sd, cfg['implicit_args'], q, abstract, glob, chunk=4096)
+            forward(q)
         dt = time.perf_counter() - t0
     value = sample * args.steps / dt
-    desc = '%d of %d grid queries per step (evenly strided), decoder only, scene encoding resident' % (
-        sample, q_all.shape[0])
+    desc = '%d of %d grid queries per step (evenly strided, mini-batches of 4096), decoder only, scene encoding ' \
+           'resident; %s' % (sample, q_all.shape[0], 'unmodified reference module (oracle/_ref copy of model/implicit.py)'
+                             if kind == 'reference' else 'oracle port')
     line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
             'data': 'synthetic', 'config': workload_config(args.batch),
-            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': kind,
                              'sample': desc},
             'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line))
+
+
+def family_profile(lib, step_fn):
+    """Per-kernel-family device time of one call of step_fn: library-side CUDA-event pairs on the launching stream
+    around every launch (o4d_profile_enable)."""
+    import ctypes
+    lib.o4d_profile_enable(1)
+    step_fn()
+    torch.cuda.synchronize()
+    n = len(FAMILIES)
+    ms_a, fl_a, ct_a = (ctypes.c_double * n)(), (ctypes.c_double * n)(), (ctypes.c_int64 * n)()
+    lib.o4d_profile_read(n, ms_a, fl_a, ct_a)
+    lib.o4d_profile_enable(0)
+    return {FAMILIES[i]: {'ms': ms_a[i], 'launches': ct_a[i], 'tflops': (fl_a[i] / ms_a[i] / 1e9) if ms_a[i] > 0 else 0.0}
+            for i in range(n) if ct_a[i]}
+
+
+def measured_peak():
+    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.isfile(peaks_path):
+        pk = json.load(open(peaks_path))
+        return float(pk['bf16_tflops_sustained']), 'MEASURED_PEAKS.json bf16_tflops_sustained'
+    return 1400.0, 'fallback (B200_PROFILING.md sustained ~1.4 PFLOP/s)'
+
+
+def carla_config3(dev, lib, batch, steps):
+    """BASELINE.json configs[2] throughput: CARLA-4D shape, abstract_levels=2 -> M = 2124 abstract points (4x the
+    GREATER cloud), d_out = 18 (13-class segmentation head), 541,314 grid queries, same decoder loop."""
+    from o4d import ops
+    from tests import configs
+    cfg = configs.C3_CARLA
+    z = np.load(os.path.join(ROOT, 'tests', 'golden', 'c3_carla_seeded.npz'))
+    abstract, glob = torch.from_numpy(z['abstract']).to(dev), torch.from_numpy(z['glob']).to(dev)
+    _, dec = configs.build_modules(cfg, dev)
+    q = configs.synthetic_queries(cfg).to(dev)
+    nq, d_out = q.shape[0], cfg['implicit_args']['d_out']
+    scene = dec.o4d_scene(abstract, glob)
+    dcfg, dparams = dec.o4d_config(), dec.o4d_params()
+    out = torch.empty((nq, d_out), dtype=torch.float32, device=dev)
+
+    def step():
+        for s0 in range(0, nq, batch):
+            ops.decoder_forward(dcfg, dparams, scene, q[s0:s0 + batch], want_penult=False, out=out[s0:s0 + batch])
+
+    step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    fam = family_profile(lib, step)
+    top = max(fam, key=lambda k: fam[k]['ms'])
+    peak, _ = measured_peak()
+    sel = torch.linspace(0, nq - 1, 4096).long().to(dev)        # the golden subset of the reference (make_golden.py)
+    gold = torch.from_numpy(z['out']).to(dev)
+    return {'queries_per_s': nq / (ms / 1e3), 'ms_per_step': ms, 'queries_per_step': nq, 'm_abstract': int(abstract.shape[0]),
+            'd_out': d_out, 'kernel_families': fam,
+            'roofline': {'bound': 'tensor', 'kernel': top, 'achieved': fam[top]['tflops'], 'peak': peak, 'unit': 'TFLOP/s',
+                         'frac': fam[top]['tflops'] / peak},
+            'max_rel_err_vs_reference_golden': float((out[sel] - gold).abs().max() / gold.abs().max())}
+
+
+def strong_scaling(dev, world, rank, enc, dec, pcl, cfg, frames=2):
+    """BASELINE.json configs[3] / SURVEY 8e: ONE frame of 2,097,152 `random` queries split contiguously over the
+    ranks (o4d.parallel.decode_sharded: no data-path collective, one all_gather_into_tensor of the output shards),
+    implicit_batch_size in {8192, 32768, 131072}.  The timed region is the whole frame as eval/inference.py runs
+    it: encoder (replicated on every rank) + prepare_scene + this rank's mini-batches + the all-gather.  Rank 0 also
+    decodes the whole frame alone and compares bit for bit."""
+    import torch.distributed as dist
+    from o4d import geometry, ops, parallel
+    state = np.random.get_state()
+    np.random.seed(cfg['seed'])
+    q_np = geometry.sample_implicit_points_blind_numpy(2097152, cfg['min_z'], cfg['cr_cube_bounds'], 3, cfg['kind'],
+                                                       cfg['cube_mode'], 'random')
+    np.random.set_state(state)
+    q_all = torch.from_numpy(q_np).to(dev)
+    dcfg, dparams = dec.o4d_config(), dec.o4d_params()
+    res = {'queries': int(q_all.shape[0]), 'frames_timed': frames, 'by_batch': {}}
+    gathered = None
+    enc_ms = None
+    for bs in (8192, 32768, 131072):
+        def frame():
+            abstract, glob, _ = enc(pcl[None], False)
+            a, g = abstract[0].contiguous(), glob[0].contiguous()
+            scene = dec.o4d_scene(a, g)                               # new tensors -> prepare_scene runs every frame
+
+            def fn(b):
+                return ops.decoder_forward(dcfg, dparams, scene, b, want_penult=False)[0]
+            return parallel.decode_sharded(fn, q_all, bs), (a, g, scene)
+
+        frame()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(frames):
+            gathered, keep = frame()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / frames], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        res['by_batch'][str(bs)] = {'ms_per_frame': ms, 'queries_per_s': q_all.shape[0] / (ms / 1e3)}
+    # replicated (un-sharded) part of a frame, timed on its own: the limiter of the 1 -> 8 curve
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        abstract, glob, _ = enc(pcl[None], False)
+        dec.o4d_scene(abstract[0].contiguous(), glob[0].contiguous())
+    e1.record()
+    torch.cuda.synchronize()
+    res['replicated_encoder_plus_prepare_ms'] = e0.elapsed_time(e1) / 3
+    if rank == 0:
+        a, g, scene = keep
+        single = torch.cat([ops.decoder_forward(dcfg, dparams, scene, q_all[s0:s0 + 131072], want_penult=False)[0]
+                            for s0 in range(0, q_all.shape[0], 131072)])
+        res['sharded_equals_single_rank_bitwise'] = bool(torch.equal(gathered, single))
+        res['max_abs_diff_sharded_vs_single'] = float((gathered - single).abs().max())
+    res['what'] = ('strong scaling: 2,097,152 random queries of ONE frame, contiguous shards over %d rank(s), encoder + '
+                   'prepare_scene replicated and inside the timed region, one all_gather_into_tensor' % world)
+    return res
+
+
+def second_device_check(dev):
+    """One process, two GPUs (the nn.DataParallel caller of train.py:305): a small decoder forward on another visible
+    device after this rank's own must give the same bits (per-device kernel attributes, per-device workspaces)."""
+    from tests import configs
+    n_dev = torch.cuda.device_count()
+    if n_dev < 2:
+        return None
+    other = torch.device('cuda', (dev.index + 1) % n_dev)
+    cfg = configs.C1_GREATER
+    z = np.load(os.path.join(ROOT, 'tests', 'golden', 'c1_greater_seeded.npz'))
+    outs = []
+    for d in (dev, other):
+        _, dec = configs.build_modules(cfg, d)
+        with torch.cuda.device(d), torch.no_grad():
+            o, _ = dec(torch.from_numpy(z['query']).to(d), torch.from_numpy(z['abstract']).to(d),
+                       torch.from_numpy(z['glob']).to(d), None)
+            torch.cuda.synchronize(d)
+        outs.append(o.cpu())
+    gold = torch.from_numpy(z['out'])
+    return {'devices': [str(dev), str(other)], 'bit_identical': bool(torch.equal(outs[0], outs[1])),
+            'max_rel_err_vs_reference_golden': float((outs[1] - gold).abs().max() / gold.abs().max())}
 
 
 def sampler_and_loss_timing(dev):
@@ -432,23 +706,9 @@ def run_o4d(args):
         # ---- roofline of the dominant kernel family: one extra profiled step right after
         roofline, families = None, None
         if rank == 0:
-            lib.o4d_profile_enable(1)
-            step_device(comm=False)                          # rank 0 only: no collective here
-            torch.cuda.synchronize()
-            import ctypes
-            n = len(FAMILIES)
-            ms_a, fl_a, ct_a = (ctypes.c_double * n)(), (ctypes.c_double * n)(), (ctypes.c_int64 * n)()
-            lib.o4d_profile_read(n, ms_a, fl_a, ct_a)
-            lib.o4d_profile_enable(0)
-            families = {FAMILIES[i]: {'ms': ms_a[i], 'launches': ct_a[i], 'tflops': (fl_a[i] / ms_a[i] / 1e9) if ms_a[i] > 0 else 0.0}
-                        for i in range(n) if ct_a[i]}
+            families = family_profile(lib, lambda: step_device(comm=False))     # rank 0 only: no collective here
             top = max(families, key=lambda k: families[k]['ms'])
-            peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
-            if os.path.isfile(peaks_path):
-                pk = json.load(open(peaks_path))
-                peak, which = float(pk['bf16_tflops_sustained']), 'MEASURED_PEAKS.json bf16_tflops_sustained'
-            else:
-                peak, which = 1400.0, 'fallback (B200_PROFILING.md sustained ~1.4 PFLOP/s)'
+            peak, which = measured_peak()
             step_total = sum(f['ms'] for f in families.values())
             ach = families[top]['tflops']
             traffic = None
@@ -463,6 +723,28 @@ def run_o4d(args):
                         'avg_launch_ms': families[top]['ms'] / families[top]['launches'],
                         'measured': 'CUDA events around every launch of the family, one extra step after the timed region',
                         'whole_step_algorithmic_tflops': FLOP_PER_QUERY * value / world / 1e12}
+        # ---- BASELINE configs[3]: strong scaling of one 2 M-query frame (every rank takes part)
+        strong = None
+        if not args.no_strong_scaling:
+            try:
+                strong = strong_scaling(dev, world, rank, enc, dec, pcl, cfg)
+            except Exception as exc:           # noqa: BLE001 -- side measurement
+                strong = {'error': '%s: %s' % (type(exc).__name__, exc)}
+        # ---- BASELINE configs[2]: CARLA-shape throughput (rank 0)
+        carla = None
+        if rank == 0 and not args.no_carla:
+            try:
+                carla = carla_config3(dev, lib, batch, max(1, min(args.steps, 3)))
+            except Exception as exc:           # noqa: BLE001
+                carla = {'error': '%s: %s' % (type(exc).__name__, exc)}
+        second_dev = None
+        if rank == 0 and world > 1:
+            try:
+                second_dev = second_device_check(dev)
+            except Exception as exc:           # noqa: BLE001
+                second_dev = {'error': '%s: %s' % (type(exc).__name__, exc)}
+        if world > 1:
+            dist.barrier()
 
     train = None
     if not args.no_train_step:
@@ -471,22 +753,22 @@ def run_o4d(args):
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, secs, threads = cpu_reference_rate(args.cpu_sample)
-        cpu_base = {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-                    'sample': '%d of %d grid queries (evenly strided), decoder only, oracle port torch-CPU fp32, '
-                              '%.1f s' % (args.cpu_sample, nq, secs)}
-    torch_gpu = None
+        rate, secs, threads, kind = cpu_reference_rate(args.cpu_sample)
+        cpu_base = {'value': rate, 'unit': UNIT, 'cores': threads, 'kind': kind,
+                    'sample': '%d of %d grid queries (evenly strided, mini-batches of 4096), decoder only, %s, torch '
+                              'CPU fp32, %.1f s' % (args.cpu_sample, nq, 'unmodified reference module (oracle/_ref)'
+                                                    if kind == 'reference' else 'oracle port', secs)}
+    torch_gpu, enc_base = None, None
     if rank == 0 and world == 1 and not args.no_torch_gpu_baseline:
-        try:                                   # a reported baseline: never allowed to take the bench line down
-            with torch.no_grad():
-                torch_gpu, q_s, ref_s = torch_eager_gpu_rate(dev, dec, abstract, glob, q_dev, batch)
-                ours = torch.cat([ops.decoder_forward(dcfg, dparams, scene, q_s[s:s + batch], want_penult=False)[0]
-                                  for s in range(0, q_s.shape[0], batch)])
-            torch_gpu['o4d_over_torch_eager'] = value / torch_gpu['value']
-            torch_gpu['max_rel_err_vs_torch_eager'] = float((ours - ref_s).abs().max() / ref_s.abs().max())
-            del q_s, ref_s, ours
+        try:                                   # reported baselines: never allowed to take the bench line down
+            torch_gpu = reference_decoder_gpu(dev, cfg, abstract, glob, q_host, batch, value, out_dev)
         except Exception as exc:               # noqa: BLE001
             torch_gpu = {'error': '%s: %s' % (type(exc).__name__, exc)}
+        try:
+            torch.cuda.empty_cache()
+            enc_base = reference_encoder_baselines(dev, cfg, pcl.cpu(), cpu=not args.no_cpu_baseline)
+        except Exception as exc:               # noqa: BLE001
+            enc_base = {'error': '%s: %s' % (type(exc).__name__, exc)}
     if rank == 0:
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
@@ -497,7 +779,9 @@ def run_o4d(args):
                         'bit_identical_to_device_path': e2e_matches},
                 'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'kernel_families': families,
                 'cpu_baseline': cpu_base, 'torch_gpu_baseline': torch_gpu,
-                'encoder': {'pts_per_s': cfg['n_points'] / (enc_ms / 1e3), 'ms': enc_ms, 'n_points': cfg['n_points']},
+                'encoder': {'pts_per_s': cfg['n_points'] / (enc_ms / 1e3), 'ms': enc_ms, 'n_points': cfg['n_points'],
+                            'reference': enc_base},
+                'carla_config3': carla, 'strong_scaling': strong, 'second_device_in_process': second_dev,
                 'train_step': train, 'tcgen05': bool(lib.o4d_has_tcgen05())}
         print(json.dumps(line))
     if world > 1:
@@ -515,6 +799,8 @@ def main():
     ap.add_argument('--cpu-sample', type=int, default=196608)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-train-step', action='store_true', help='skip the config-5 training-step timing')
+    ap.add_argument('--no-strong-scaling', action='store_true', help='skip the 2 M-query strong-scaling frames')
+    ap.add_argument('--no-carla', action='store_true', help='skip the CARLA config-3 throughput key')
     ap.add_argument('--no-torch-gpu-baseline', action='store_true',
                     help='skip the PyTorch-eager timing of the same decoder on the same GPU')
     args = ap.parse_args()

@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fused_kernel(const Params p) 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = smem_u32(smem);
 
-    if (threadIdx.x == 0 && blockIdx.x == gridDim.x / 2) { g_dbg[4] = clock64(); g_dbg[9] = 0; }
+    if (O4D_STAMPS && threadIdx.x == 0 && blockIdx.x == gridDim.x / 2) { g_dbg[4] = clock64(); g_dbg[9] = 0; }
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) { mbar_init(BAR(W_FULL + i), 1); mbar_init(BAR(W_EMPTY + i), 1); }
         for (int i = 0; i < WC_STAGES; ++i) { mbar_init(BAR(WC_FULL + i), 1); mbar_init(BAR(WC_EMPTY + i), 1); }
@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fused_kernel(const Params p) 
         const int qi_rd = min(qi, p.tq - 1);                            // padding rows read a real query's slice
         const uint32_t rd_k = OFF_G + r * G_PITCH + half * 64;
         const uint32_t rd_q = OFF_G + (BM + qi_rd) * G_PITCH + half * 64;
-        const bool dbg = (blockIdx.x == gridDim.x / 2) && threadIdx.x == 0;
+        const bool dbg = O4D_STAMPS && (blockIdx.x == gridDim.x / 2) && threadIdx.x == 0;
         if (dbg) g_dbg[0] = clock64();
         for (int c = 0; c < NC; ++c) {
             const int b = c % NBUF;
@@ -587,8 +587,8 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fused_kernel(const Params p) 
                         const uint64_t w_lo = w_hi + (uint64_t)((d * 64) >> 4);
                         umma_f16_ts(dcol, a_hi, w_hi, idescN, (c | ks) ? 1u : 0u);
                         if (split) {
-                            umma_f16_ts(dcol, a_lo, w_hi, idescN, 1u);
-                            umma_f16_ts(dcol, a_hi, w_lo, idescN, 1u);
+                            if (split != 3) umma_f16_ts(dcol, a_lo, w_hi, idescN, 1u);   // split 3: hidden rounded to bf16
+                            if (split != 2) umma_f16_ts(dcol, a_hi, w_lo, idescN, 1u);   // split 2: W_a2 rounded to bf16
                         }
                     }
                 }
@@ -730,6 +730,10 @@ __global__ void fused_pack_kernel(const float* __restrict__ wc, const float* __r
 
 }  // namespace fa
 
+// Experiment knob (diagnostics, o4d_debug_set_fused_passes): which of the three bf16x3 products the logits
+// contraction issues.  1 = all three (default), 2 = drop hidden_hi * W_lo, 3 = drop hidden_lo * W_hi.
+static std::atomic<int> g_fused_mma2_mode{1};
+
 bool attn_fused_supported(int d, int k) {
     if (d % 32 != 0 || d < 288 || d > 416 || k < 8 || k > O4D_MAX_K) return false;  // k >= 8: at most 16 queries per tile
     const int dn = d > 256 ? d / 2 : d;
@@ -755,14 +759,10 @@ int attn_fused_launch(const PtBlockParams& P, const AttnTables& T, const float* 
                       int precision, cudaStream_t st) {
     if (n == 0) return 0;
     O4D_REQUIRE(attn_fused_supported(d, k) && T.fused, "fused attention: unsupported shape or missing weights");
-    static bool attr_done = false;
-    if (!attr_done) {
-        O4D_CUDA(cudaFuncSetAttribute(fa::attn_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        O4D_CUDA(cudaFuncSetAttribute(fa::attn_fused_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        O4D_CUDA(cudaFuncSetAttribute(fa::attn_fused_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        O4D_CUDA(cudaFuncSetAttribute(fa::attn_fused_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_done = true;
-    }
+    O4D_SMEM_ATTR(fa::attn_fused_kernel<0>, 227 * 1024);
+    O4D_SMEM_ATTR(fa::attn_fused_kernel<12>, 227 * 1024);
+    O4D_SMEM_ATTR(fa::attn_fused_kernel<14>, 227 * 1024);
+    O4D_SMEM_ATTR(fa::attn_fused_kernel<16>, 227 * 1024);
     const int NC = 2 * d / fa::HC;
     fa::Params p;
     p.pos = pos; p.ldpos = ldpos; p.pos2 = pos2; p.ldpos2 = ldpos2; p.nbr = nbr;
@@ -771,7 +771,7 @@ int attn_fused_launch(const PtBlockParams& P, const AttnTables& T, const float* 
     p.wmain = (const uint8_t*)T.fused;
     p.wp2 = (const uint8_t*)T.fused + align_up((size_t)NC * fa::wstage_bytes(d), 256);
     p.out = out;
-    p.n = n; p.d = d; p.k = k; p.tq = fa::BM / k; p.split = (precision == 1) ? 1 : 0;
+    p.n = n; p.d = d; p.k = k; p.tq = fa::BM / k; p.split = (precision == 1) ? g_fused_mma2_mode.load(std::memory_order_relaxed) : 0;
     p.scale_log2 = (float)(1.4426950408889634 / sqrt((double)d));
     const int64_t tiles = cdiv(n, p.tq);
     // algorithmic flops of what this launch replaces (reference formulation): per pair 2*(3*32 + 32*d) +
@@ -791,6 +791,7 @@ int attn_fused_launch(const PtBlockParams& P, const AttnTables& T, const float* 
 
 }  // namespace o4d
 
+extern "C" void o4d_debug_set_fused_passes(int mode) { o4d::g_fused_mma2_mode.store(mode >= 1 && mode <= 3 ? mode : 1); }
 extern "C" int o4d_debug_read(long long* out16) {
     return (int)cudaMemcpyFromSymbol(out16, o4d::fa::g_dbg, sizeof(long long) * 16);
 }

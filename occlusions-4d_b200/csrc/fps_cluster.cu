@@ -163,11 +163,7 @@ fps_cluster_kernel(const float* __restrict__ xyz, int n, int64_t ld, int n_out, 
 template <int CTAS, int P>
 static int fps_cluster_launch_t(const float* xyz, int64_t n, int64_t ld, int64_t n_out, int64_t start, int32_t* counts,
                                 int64_t* order64, size_t smem, cudaStream_t st) {
-    static bool attr_done = false;
-    if (!attr_done) {
-        O4D_CUDA(cudaFuncSetAttribute(fc::fps_cluster_kernel<CTAS, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_done = true;
-    }
+    O4D_SMEM_ATTR((fc::fps_cluster_kernel<CTAS, P>), 200 * 1024);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(CTAS, 1, 1);
     cfg.blockDim = dim3(fc::THREADS, 1, 1);

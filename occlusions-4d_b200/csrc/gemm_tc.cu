@@ -246,7 +246,7 @@ linear_tc_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda, 
             }
         };
         float cur[GPW][8], nxt[GPW][8];
-        const bool dbg = (blockIdx.x == gridDim.x / 2) && blockIdx.y == 0 && threadIdx.x == 0;
+        const bool dbg = O4D_STAMPS && (blockIdx.x == gridDim.x / 2) && blockIdx.y == 0 && threadIdx.x == 0;
         if (dbg) g_dbg_tc[0] = clock64();
         load_chunk(0, cur);
         for (int c = 0; c < nchunks; ++c) {
@@ -434,13 +434,6 @@ linear_tc_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda, 
 
 }  // namespace tc
 
-// 2-CTA (cta_group::2) variant, gemm_tc2.cu.  O4D_TC_PAIR=0/1 selects it for every weight whose tile is at
-// least 32 columns wide; the packed-weight format differs (each CTA of a pair copies half of the tile's rows),
-// so packing and launching consult the same predicate.
-int tc2_pack_launch(const float* W, int64_t n, int64_t k, int64_t ldw, void* packed, cudaStream_t st);
-int linear_tc2_packed_launch(const float* A, int64_t rows, int64_t k, int64_t lda, const void* packed, int64_t n,
-                             const float* bias, const float* R, int64_t ldr, float* C, int64_t ldc, int flags,
-                             int precision, cudaStream_t st, const RowGather* gp);
 // Persistent warp-specialized variant, gemm_tcp.cu (same packed-weight format).  Opt-in (O4D_TC_PERSIST=1):
 // parity green, but measured slower than this kernel (dense family 27.8 vs 22.0 ms per step, see gemm_tcp.cu).
 int linear_tcp_packed_launch(const float* A, int64_t rows, int64_t k, int64_t lda, const void* packed, int64_t n,
@@ -456,19 +449,9 @@ static bool tc_persistent(int64_t rows, int64_t n, int64_t ktot) {
     return v == 1 && cdiv(rows, tc::BM) * tc::pack_meta((int)n, (int)ktot).ntiles >= 2 * 148;
 }
 
-static bool tc_pair(int64_t n, int64_t k) {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("O4D_TC_PAIR");
-        v = (e && e[0] == '1') ? 1 : 0;
-    }
-    return v == 1 && tc::pack_meta((int)n, (int)k).bn >= 32;
-}
-
 size_t tc_pack_bytes(int64_t n, int64_t k) { return tc::pack_bytes(tc::pack_meta((int)n, (int)k)); }
 
 int tc_pack_launch(const float* W, int64_t n, int64_t k, int64_t ldw, void* packed, cudaStream_t st) {
-    if (tc_pair(n, k)) return tc2_pack_launch(W, n, k, ldw, packed, st);
     tc::PackMeta m = tc::pack_meta((int)n, (int)k);
     const int64_t total = (int64_t)m.ntiles * m.kchunks * m.bn * tc::BK;
     int64_t blocks = cdiv(total, 256);
@@ -487,17 +470,11 @@ int linear_tc_packed_launch(const float* A, int64_t rows, int64_t k, int64_t lda
                             int precision, cudaStream_t st, const RowGather* gp) {
     if (rows == 0) return 0;
     const int64_t ktot_ = gp && gp->a2 ? cdiv(k, tc::BK) * tc::BK + gp->k2 : k;
-    if (tc_pair(n, ktot_))
-        return linear_tc2_packed_launch(A, rows, k, lda, packed, n, bias, R, ldr, C, ldc, flags, precision, st, gp);
     if (tc_persistent(rows, n, ktot_))
         return linear_tcp_packed_launch(A, rows, k, lda, packed, n, bias, R, ldr, C, ldc, flags, precision, st, gp);
     RowGather g;
     if (gp) g = *gp;
-    static bool attr_done = false;
-    if (!attr_done) {
-        O4D_CUDA(cudaFuncSetAttribute(tc::linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-        attr_done = true;
-    }
+    O4D_SMEM_ATTR(tc::linear_tc_kernel, tc::SMEM_BYTES);
     // with a K-concatenated second operand the packed weight spans round32(k) + k2 columns
     const int64_t ktot = g.a2 ? cdiv(k, tc::BK) * tc::BK + g.k2 : k;
     tc::PackMeta m = tc::pack_meta((int)n, (int)ktot);

@@ -186,7 +186,7 @@ linear_tcp_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda,
         const bool vec_ok = !g.qa && (m.n % 4 == 0) && (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) &&
                             (!R || ((ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(R) & 15) == 0))) &&
                             (!bias || ((reinterpret_cast<uintptr_t>(bias) & 15) == 0));
-        const bool dbg = blockIdx.x == gridDim.x / 2 && ew == 0 && lane == 0;
+        const bool dbg = O4D_STAMPS && blockIdx.x == gridDim.x / 2 && ew == 0 && lane == 0;
         for (int ti = 0; ti < my_tiles; ++ti) {
             const int T = (int)blockIdx.x + ti * (int)gridDim.x;
             const int64_t row0 = (int64_t)(T / m.ntiles) * BM;
@@ -350,11 +350,7 @@ int linear_tcp_packed_launch(const float* A, int64_t rows, int64_t k, int64_t ld
     if (rows == 0) return 0;
     RowGather g;
     if (gp) g = *gp;
-    static bool attr_done = false;
-    if (!attr_done) {
-        O4D_CUDA(cudaFuncSetAttribute(tcp::linear_tcp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tcp::SMEM_BYTES));
-        attr_done = true;
-    }
+    O4D_SMEM_ATTR(tcp::linear_tcp_kernel, tcp::SMEM_BYTES);
     const int64_t ktot = g.a2 ? cdiv(k, tcp::BK) * tcp::BK + g.k2 : k;   // K-concatenated second operand
     tcp::PackMeta m = tcp::pack_meta((int)n, (int)ktot);
     const int64_t total = cdiv(rows, tch::BM) * m.ntiles;

@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <atomic>
 #include "../../include/o4d.h"
 
 namespace o4d {
@@ -28,6 +29,12 @@ void set_error(const char* fmt, ...);
         }                                                                           \
     } while (0)
 
+// In-kernel cycle stamps (clock64 into __device__ globals, read by o4d_debug_read*) are a bottleneck-hunting
+// tool: compiled OUT of release builds.  `make STAMPS=1` (-DO4D_STAMPS=1) turns them on for tools/stamps_*.py.
+#ifndef O4D_STAMPS
+#define O4D_STAMPS 0
+#endif
+
 void count_launch();  // diagnostics: kernels launched by this library (o4d_launch_count)
 
 // Opt-in kernel-family timer (o4d_profile_enable): CUDA events on the launching stream.
@@ -48,6 +55,21 @@ struct ProfScope {
                              cudaGetErrorString(e__), __FILE__, __LINE__);          \
             return (int)e__;                                                        \
         }                                                                           \
+    } while (0)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: set it once per (call site, device).
+// A process-wide flag would leave the second GPU a process uses (nn.DataParallel in train.py:305) on the 48 KB
+// default.  One byte per device, written after the call succeeded; racing threads at worst both set it.
+#define O4D_SMEM_ATTR(kernel, bytes)                                                               \
+    do {                                                                                           \
+        static std::atomic<unsigned char> done__[64];                                              \
+        int dev__ = 0;                                                                             \
+        O4D_CUDA(cudaGetDevice(&dev__));                                                           \
+        const bool slot__ = dev__ >= 0 && dev__ < 64;                                              \
+        if (!slot__ || !done__[dev__].load(std::memory_order_acquire)) {                           \
+            O4D_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+            if (slot__) done__[dev__].store(1, std::memory_order_release);                         \
+        }                                                                                          \
     } while (0)
 
 #define O4D_TRY(expr)                  \

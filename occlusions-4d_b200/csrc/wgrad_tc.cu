@@ -311,12 +311,8 @@ int wgrad_tc_splits(int64_t rows, int64_t n, int64_t k) {
 // part must hold splits * n * k floats (wgrad_tc_splits).
 int wgrad_tc_launch(const float* dY, int64_t lddy, const float* A, int64_t lda, int64_t rows, int64_t n, int64_t k,
                     bool relu_a, int precision, float* part, int splits, cudaStream_t st) {
-    static bool attr_done = false;
-    if (!attr_done) {
-        O4D_CUDA(cudaFuncSetAttribute(wg::wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::SMEM_BYTES));
-        O4D_CUDA(cudaFuncSetAttribute(wg::wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::SMEM_BYTES));
-        attr_done = true;
-    }
+    O4D_SMEM_ATTR(wg::wgrad_tc_kernel<true>, wg::SMEM_BYTES);
+    O4D_SMEM_ATTR(wg::wgrad_tc_kernel<false>, wg::SMEM_BYTES);
     wg::Tiling t = wg::make_tiling((int)n, (int)k);
     const int64_t rps = cdiv(cdiv(rows, splits), wg::BK) * wg::BK;
     dim3 grid((unsigned)(t.ptiles * t.qtiles), (unsigned)splits);

@@ -41,7 +41,10 @@ class LinearFn(torch.autograd.Function):
         prec = _prec(precision)
         flags = (ops.RELU_IN if relu_in else 0) | (ops.RELU_OUT if relu_out else 0)
         with torch.cuda.device(x2.device):
-            y = torch.empty((x2.shape[0], n), dtype=torch.float32, device=x2.device)
+            # allocated in its final shape: a Function must not hand out a VIEW of a tensor it created (the
+            # reference's callers write into the decoder output in place, pipeline.py:196-207, and autograd
+            # rejects in-place writes to views made inside a custom Function)
+            y = torch.empty((*lead, n), dtype=torch.float32, device=x2.device)
             if x2.shape[0] > 0:        # an empty batch has no device pointers to hand over
                 rc = _lib.lib().o4d_linear_f32(_ptr(x2), x2.shape[0], k, k, _ptr(w), _ptr(b), n, _ptr(r), n,
                                                _ptr(y), n, flags, prec, _stream(x2))
@@ -49,7 +52,7 @@ class LinearFn(torch.autograd.Function):
         assert not (relu_out and residual is not None), 'linear: relu_out with a residual is not used on the path'
         ctx.save_for_backward(x2, w, y if relu_out else None)
         ctx.meta = (lead, relu_in, relu_out, prec, bias is not None, residual is not None)
-        return y.reshape(*lead, n)
+        return y
 
     @staticmethod
     def backward(ctx, dy):
@@ -69,7 +72,7 @@ class LinearFn(torch.autograd.Function):
             g = dy2
             if relu_out:
                 g = torch.empty_like(dy2)
-                _lib.check(L.o4d_relu_backward_f32(_ptr(dy2), _ptr(y), dy2.numel(), _ptr(g), st),
+                _lib.check(L.o4d_relu_backward_f32(_ptr(dy2), _ptr(y.reshape(-1, n)), dy2.numel(), _ptr(g), st),
                            'o4d_relu_backward_f32')
             dx = torch.empty((rows, k), dtype=torch.float32, device=x2.device) if need_x else None
             dw = torch.empty((n, k), dtype=torch.float32, device=x2.device) if need_w else None

@@ -18,7 +18,19 @@ def _wants_grad(module, *tensors):
         return False
     if any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors):
         return True
-    return any(p.requires_grad for p in module.parameters())
+    if any(p.requires_grad for p in module.parameters()):
+        return True
+    # nn.DataParallel replicas (train.py:305) carry their weights as plain attributes of the sub-modules, not as
+    # registered parameters: parameters() is empty there although the tensors require grad.
+    for m in module.modules():
+        for t in m.__dict__.get('_parameters', {}).values():
+            if isinstance(t, torch.Tensor) and t.requires_grad:
+                return True
+        for name in ('weight', 'bias'):
+            t = m.__dict__.get(name, None)
+            if isinstance(t, torch.Tensor) and t.requires_grad:
+                return True
+    return False
 
 
 def square_distance(src, dst):

@@ -1,6 +1,7 @@
 """TEST INFRASTRUCTURE ONLY -- imports the UNMODIFIED reference model code.
 
-Works only where ``/root/reference`` exists (the build container).  Used by
+Imports from ``/root/reference`` where it exists (the build container), else from the byte-for-byte copy
+``oracle/_ref/`` that ``oracle/make_ref.py`` makes for the GPU box (baseline timing in bench.py).  Used by
 ``tests/golden/make_golden.py`` to generate the committed golden vectors and by the
 ``not gpu`` tests that pin ``oracle/o4d_oracle.py`` against the real reference.  Nothing
 that runs on the GPU box may call this (``/root/reference`` is absent there).
@@ -14,9 +15,14 @@ import os
 import sys
 import warnings
 
-REF_ROOT = os.environ.get('O4D_REFERENCE_ROOT', '/root/reference')
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _REPO = os.path.dirname(_HERE)
+REF_ROOT = os.environ.get('O4D_REFERENCE_ROOT', '/root/reference')
+if not os.path.isfile(os.path.join(REF_ROOT, 'model', 'implicit.py')):
+    # GPU box: the byte-for-byte copy made by oracle/make_ref.py (git-ignored, shipped with the snapshot).
+    # Model code only -- no pretrained checkpoints, no data / eval / train scripts.
+    REF_ROOT = os.path.join(_HERE, '_ref')
+IS_COPY = REF_ROOT == os.path.join(_HERE, '_ref')
 
 
 def available():

@@ -106,13 +106,62 @@ def make_ckpt_fixture(ref, which):
     query = query[sel]
     enc, dec, abstract, glob, coords, out, pen = run_reference(
         ref, ck['pcl_args'], ck['implicit_args'], 0, pcl, query, state=(ck['pcl_net'], ck['implicit_net']))
+    # fp64 arbitration: the oracle in double on the reference's own abstract cloud ("fp64 via
+    # .double() copies to arbitrate").  fp32 implementations are judged by their distance to this.
+    from oracle import o4d_oracle as orc
+    sd64 = orc.cast_state(ck['implicit_net'], torch.float64)
+    out64, pen64 = orc.decoder_forward(sd64, ck['implicit_args'], query.double(), abstract.double(), glob.double(),
+                                       knn_fp32=True)
     os.makedirs(os.path.join(HERE, '_ckpt'), exist_ok=True)
     torch.save({'pcl_args': ck['pcl_args'], 'implicit_args': ck['implicit_args'],
                 'pcl_net': ck['pcl_net'], 'implicit_net': ck['implicit_net'],
                 'pcl': pcl, 'query': query, 'abstract': abstract, 'glob': glob, 'out': out,
-                'penult': pen[:, :16].contiguous()},
+                'penult': pen[:, :16].contiguous(), 'out64': out64, 'penult64': pen64[:, :16].contiguous(),
+                'max_abs_logit': out.abs().max()},
                os.path.join(HERE, '_ckpt', which + '_nets.pt'))
-    print('wrote _ckpt/%s_nets.pt' % which)
+    from tests.test_oracle import boundary_tie_free
+    ok = boundary_tie_free(query[:, :3], abstract[:, :3],
+                           [ck['implicit_args']['num_local_features'], ck['implicit_args']['cross_attn_neighbors']])
+    print('wrote _ckpt/%s_nets.pt  (largest |logit| %.1f, reference fp32 vs fp64 oracle on %d tie-free rows %.2e)'
+          % (which, float(out.abs().max()), int(ok.sum()),
+             float((out.double() - out64)[ok].abs().max() / out64[ok].abs().max())))
+
+
+def make_resnetfc_fixture(ref):
+    """ResnetFC.do_forward (implicit.py:152-208): the global-only mode LocalPclResnetFC falls back to when
+    num_local_features == 0 (implicit.py:365-367), with (B, D) and (B, N, D) features."""
+    arrays = {}
+    with ref_loader.quiet():
+        for tag, kw in {'a': dict(d_in=4, d_hidden=96, d_out=5, d_latent=48, n_blocks=3, pos_encoding_freqs=4),
+                        'b': dict(d_in=4, d_hidden=416, d_out=9, d_latent=128, n_blocks=2, pos_encoding_freqs=8)}.items():
+            torch.manual_seed(77)
+            net = ref['implicit'].ResnetFC(**kw).eval()
+            g = torch.Generator().manual_seed(5)
+            pts = torch.rand(2, 1500, 4, generator=g) * 8 - 4
+            f_glob = torch.randn(2, kw['d_latent'], generator=g)
+            f_pt = torch.randn(2, 1500, kw['d_latent'], generator=g)
+            with torch.no_grad():
+                o1, p1 = net(pts, f_glob)
+                o2, p2 = net(pts, f_pt)
+                o3, p3 = net(pts[0], f_pt[0])          # 2-D inputs are auto-batched (implicit.py:164-169)
+                # LocalPclResnetFC with num_local_features=0 routes here (implicit.py:365-367)
+                torch.manual_seed(77)
+                loc = ref['implicit'].LocalPclResnetFC(num_local_features=0, local_mode='attention',
+                                                       cross_attn_layers=0, **kw).eval()
+                o4, p4 = loc(pts, None, f_glob, None)
+            assert torch.equal(o3, o2[0])
+            if tag == 'a':      # small: full weights travel; 'b' is re-created from the seed (checksum below)
+                for k, v in net.state_dict().items():
+                    arrays['%s.sd.%s' % (tag, k)] = v
+            arrays[tag + '.checksum'] = weight_checksum(net)
+            # inputs are re-drawn in the test from the same CPU generator (seed 5): only outputs are stored
+            arrays.update({tag + '.in_checksum': np.array([float(pts.double().sum()), float(f_pt.double().sum())]),
+                           tag + '.out_glob': o1,
+                           tag + '.pen_glob': p1[..., :16].contiguous(), tag + '.out_pt': o2,
+                           tag + '.pen_pt': p2[..., :16].contiguous(), tag + '.out_local0': o4})
+            for k, v in kw.items():
+                arrays['%s.kw.%s' % (tag, k)] = np.array(v)
+    save('resnetfc_golden.npz', **arrays)
 
 
 def main():
@@ -128,11 +177,12 @@ def main():
         'c1': lambda: make_model_fixture(ref, 'c1_greater_seeded.npz', configs.C1_GREATER, False),
         'c2': lambda: make_model_fixture(ref, 'c2_greater_seeded.npz', configs.C2_GREATER, False, 4096),
         'c3': lambda: make_model_fixture(ref, 'c3_carla_seeded.npz', configs.C3_CARLA, False, 4096),
+        'resnetfc': lambda: make_resnetfc_fixture(ref),
     }
     for k, fn in todo.items():
-        if not args.only or k in args.only.split(','):
+        if (not args.only and not args.ckpt) or k in args.only.split(','):
             fn()
-    if args.ckpt:
+    if args.ckpt and args.only in ('', 'ckpt'):
         for which in ('greater', 'carla'):
             make_ckpt_fixture(ref, which)
 

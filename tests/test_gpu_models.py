@@ -204,13 +204,19 @@ def test_full_size_encoder_is_deterministic(c2):
     assert a1.shape == (1, 531, 291)
 
 
-# ------------------------------------------------------------ released checkpoints (optional)
+# ------------------------------------------------------------ released checkpoints
+
+TOL_FP64 = 1e-4     # distance to the fp64 arbitration run (the reference's own fp32 forward sits at ~2e-4)
+
 
 @pytest.mark.parametrize('which', ['greater', 'carla'])
 def test_released_checkpoint_parity(which):
+    """The released weights (pretrained/*.pth, loaded as eval/inference.py:39-73 does) through encoder and
+    decoder, against (i) the unmodified reference's fp32 outputs and (ii) the oracle run in fp64 on the same
+    neighbour sets.  Fixture: tests/golden/make_golden.py --ckpt.  A missing fixture is a FAILURE: real-weight
+    parity is part of the bar, not an optional extra."""
     path = os.path.join(GOLD, '_ckpt', which + '_nets.pt')
-    if not os.path.isfile(path):
-        pytest.skip('checkpoint fixture not generated (tests/golden/make_golden.py --ckpt)')
+    assert os.path.isfile(path), 'checkpoint fixture missing: run tests/golden/make_golden.py --ckpt'
     ck = torch.load(path, map_location='cpu', weights_only=True)
     enc = o4d.PointCompletionNetV3(**ck['pcl_args'])
     dec = o4d.LocalPclResnetFC(**ck['implicit_args'])
@@ -220,12 +226,66 @@ def test_released_checkpoint_parity(which):
     with torch.no_grad():
         a, gl, _ = enc(ck['pcl'].to(DEV)[None], False)
         out, pen = dec(ck['query'].to(DEV), ck['abstract'].to(DEV), ck['glob'].to(DEV), None)
+    out, pen = out.cpu(), pen.cpu()
     assert torch.equal(a.cpu()[0][:, :3], ck['abstract'][:, :3])
     assert relerr(a.cpu()[0], ck['abstract']) < TOL and relerr(gl.cpu()[0], ck['glob']) < TOL
+    # (i) the reference itself, on rows whose neighbour sets are unambiguous (abstract_levels=2 duplicates positions)
     ok = boundary_tie_free(ck['query'][:, :3], ck['abstract'][:, :3],
                            [ck['implicit_args']['num_local_features'], ck['implicit_args']['cross_attn_neighbors']])
-    assert relerr(out.cpu()[ok], ck['out'][ok]) < TOL
-    assert relerr(pen.cpu()[ok][:, :16], ck['penult'][ok]) < TOL
+    assert ok.float().mean() > 0.5
+    e_ref, e_ref_pen = relerr(out[ok], ck['out'][ok]), relerr(pen[ok][:, :16], ck['penult'][ok])
+    assert e_ref < TOL and e_ref_pen < TOL, (e_ref, e_ref_pen)
+    # (ii) fp64 arbitration on EVERY row (same canonical tie rule, fp32 neighbour sets)
+    e64 = relerr(out.double(), ck['out64'])
+    e64_pen = relerr(pen[:, :16].double(), ck['penult64'])
+    ref64 = relerr(ck['out'][ok].double(), ck['out64'][ok])
+    print('%s checkpoint: largest |logit| %.1f; ours vs reference %.2e, ours vs fp64 %.2e, reference vs fp64 %.2e'
+          % (which, float(out.abs().max()), e_ref, e64, ref64))
+    assert e64 < TOL_FP64 and e64_pen < TOL_FP64, (e64, e64_pen)
+    # the large-logit regime is on record (SURVEY hard part 1: GREATER logits reach several hundred)
+    assert abs(float(out.abs().max()) - float(ck['max_abs_logit'])) < 1e-2 * float(ck['max_abs_logit'])
+    if which == 'greater':
+        assert float(ck['max_abs_logit']) > 100.0
+    assert bool(torch.isfinite(out).all())
+
+
+# ------------------------------------------------------------ ResnetFC.do_forward
+
+@pytest.mark.parametrize('tag', ['a', 'b'])
+def test_resnetfc_global_mode_matches_reference_golden(tag):
+    """implicit.py:152-208: global-only conditioning, (B, D) and (B, N, D) features, 2-D inputs, and the
+    num_local_features == 0 route of LocalPclResnetFC (implicit.py:365-367)."""
+    g = load('resnetfc_golden.npz')
+    kw = {k.split('.kw.')[1]: int(v) for k, v in g.items() if k.startswith(tag + '.kw.')}
+    torch.manual_seed(77)
+    net = o4d.ResnetFC(**kw).eval()
+    if tag == 'a':
+        net.load_state_dict({k.split('.sd.')[1]: v for k, v in g.items() if k.startswith(tag + '.sd.')}, strict=True)
+    assert np.allclose(configs.weight_checksum(net), g[tag + '.checksum'].numpy(), rtol=0, atol=1e-9)
+    gen = torch.Generator().manual_seed(5)
+    pts = torch.rand(2, 1500, 4, generator=gen) * 8 - 4
+    f_glob = torch.randn(2, kw['d_latent'], generator=gen)
+    f_pt = torch.randn(2, 1500, kw['d_latent'], generator=gen)
+    assert np.allclose([float(pts.double().sum()), float(f_pt.double().sum())], g[tag + '.in_checksum'].numpy())
+    net = net.to(DEV)
+    with torch.no_grad():
+        o1, p1 = net(pts.to(DEV), f_glob.to(DEV))
+        o2, p2 = net(pts.to(DEV), f_pt.to(DEV))
+        o3, p3 = net(pts[0].to(DEV), f_pt[0].to(DEV))
+        torch.manual_seed(77)
+        loc = o4d.LocalPclResnetFC(num_local_features=0, local_mode='attention', cross_attn_layers=0, **kw).eval()
+        if tag == 'a':
+            loc.load_state_dict(net.state_dict(), strict=True)
+        o4, _ = loc.to(DEV)(pts.to(DEV), None, f_glob.to(DEV), None)
+    assert o1.shape == (2, 1500, kw['d_out']) and p1.shape == (2, 1500, kw['d_hidden'])
+    assert o3.shape == (1500, kw['d_out']) and torch.equal(o3, o2[0])
+    for got, want in ((o1, g[tag + '.out_glob']), (p1[..., :16], g[tag + '.pen_glob']), (o2, g[tag + '.out_pt']),
+                      (p2[..., :16], g[tag + '.pen_pt']), (o4, g[tag + '.out_local0'])):
+        assert relerr(got.cpu(), want) < TOL_TIGHT, relerr(got.cpu(), want)
+    with pytest.raises(AssertionError):
+        net(pts.to(DEV), f_glob[:1].to(DEV))                 # batch mismatch (implicit.py:171)
+    with pytest.raises(AssertionError):
+        net(pts.to(DEV), f_pt[:, :10].to(DEV))               # per-point features of the wrong length (:176)
 
 
 # ------------------------------------------------------------ fused attention kernel coverage

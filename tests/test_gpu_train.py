@@ -5,6 +5,7 @@ differentiable), i.e. exactly what the reference's train.py gets from its eager 
 Tolerance: max|ours - ref| / max|ref| per gradient tensor <= 1e-3 (north-star bar); the fp32 /
 bf16x3 kernels deliver ~1e-5, the scatter-adds use float atomics (order-dependent rounding)."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -249,6 +250,48 @@ def test_model_gradients_match_oracle_autograd(cfg, prec):
     den = sum(float(sd[n_].grad.pow(2).sum()) for mod, sd in ((enc, sd_e), (dec, sd_d))
               for n_, p in mod.named_parameters())
     assert math.sqrt(num / den) < 3e-3, math.sqrt(num / den)
+
+
+@pytest.mark.parametrize('color_mode', ['rgb', 'rgb_nosigmoid', 'hsv'])
+def test_callers_in_place_squashing_of_the_grad_enabled_output(color_mode):
+    """pipeline.py:193-207 writes into the decoder output IN PLACE (sigmoid / clamp of the colour channels) while
+    grad mode is on, through the batched 5-argument call form, then backpropagates.  The output must therefore
+    not be a view created inside a custom autograd.Function; gradients must match the oracle's autograd."""
+    cfg = configs.TINY_CARLA if color_mode == 'hsv' else configs.TINY_GREATER
+    cfg = dict(cfg, implicit_args=dict(cfg['implicit_args'], d_out=16 if color_mode == 'hsv' else 5))
+    enc, dec = configs.build_modules(cfg, DEV)
+    dec.train()
+    dec.o4d_precision = 0
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', cfg['name'] + '.npz'))
+    query, abstract, glob = configs.synthetic_queries(cfg), torch.from_numpy(z['abstract']), torch.from_numpy(z['glob'])
+
+    def squash(o):          # verbatim data flow of pipeline.py:199-207
+        if color_mode == 'rgb':
+            o[..., 1:4] = torch.sigmoid(o[..., 1:4])
+        elif color_mode == 'rgb_nosigmoid':
+            o[..., 1:4] = torch.clamp(o[..., 1:4].clone(), min=0.0, max=1.0)
+        else:
+            o[..., 13:15] = torch.clamp(o[..., 13:15].clone(), min=0.0, max=1.0)
+        return o
+
+    out, pen, extra = dec(query.to(DEV)[None], abstract.to(DEV)[None], glob.to(DEV)[None], None, False)
+    assert extra is None and out.requires_grad
+    out = squash(out)
+    gen = torch.Generator().manual_seed(11)
+    w = torch.randn(out.shape, generator=gen)
+    (out * w.to(DEV)).sum().backward()
+    # oracle: same weights, same squashing, torch.autograd on the CPU in fp64
+    sd = {k: v.detach().double().cpu().requires_grad_(True) for k, v in dec.state_dict().items()}
+    o_ref, _ = orc.decoder_forward(sd, cfg['implicit_args'], query.double(), abstract.double(), glob.double(),
+                                   knn_fp32=True)
+    o_ref = squash(o_ref[None].clone())
+    (o_ref * w.double()).sum().backward()
+    assert rel(out.detach(), o_ref.detach()) < 1e-4
+    for name, p in dec.named_parameters():
+        assert p.grad is not None, name
+        ref = sd[name].grad
+        if float(ref.abs().max()) > 1e-12:
+            assert rel(p.grad, ref) < TOL, (name, rel(p.grad, ref))
 
 
 def test_train_and_inference_paths_agree_and_directional_derivative_c2_widths():

@@ -202,3 +202,19 @@ def test_query_grid_matches_live_reference():
         theirs = ref['geometry'].sample_implicit_points_blind_numpy(
             n, cfg['min_z'], cfg['cr_cube_bounds'], 3, cfg['kind'], cfg['cube_mode'], mode)
         assert np.array_equal(ours, theirs)
+
+
+def test_resnetfc_oracle_matches_reference_golden():
+    """the global-only mode (implicit.py:152-208) against outputs of the unmodified reference."""
+    g = load('resnetfc_golden.npz')
+    kw = {k.split('.kw.')[1]: int(v) for k, v in g.items() if k.startswith('a.kw.')}
+    sd = {k.split('.sd.')[1]: v for k, v in g.items() if k.startswith('a.sd.')}
+    gen = torch.Generator().manual_seed(5)
+    pts = torch.rand(2, 1500, 4, generator=gen) * 8 - 4
+    f_glob = torch.randn(2, kw['d_latent'], generator=gen)
+    f_pt = torch.randn(2, 1500, kw['d_latent'], generator=gen)
+    o1, p1 = orc.resnetfc_forward(sd, kw, pts, f_glob)
+    o2, p2 = orc.resnetfc_forward(sd, kw, pts, f_pt)
+    assert relerr(o1, g['a.out_glob']) < 1e-5 and relerr(p1[..., :16], g['a.pen_glob']) < 1e-5
+    assert relerr(o2, g['a.out_pt']) < 1e-5 and relerr(p2[..., :16], g['a.pen_pt']) < 1e-5
+    assert relerr(o1, g['a.out_local0']) < 1e-5

@@ -53,6 +53,13 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t_begin = self.t_end = None
+
+    def mark_begin(self):
+        self.t_begin = time.monotonic()
+
+    def mark_end(self):
+        self.t_end = time.monotonic()
 
     def start(self):
         try:
@@ -66,7 +73,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
+            self.rows.append((time.monotonic(), [c.strip() for c in line.split(',')]))
 
     def stop(self):
         if self.proc is None:
@@ -77,7 +84,10 @@ class ClockSampler:
         except Exception:
             pass
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        inside = [r for t, r in self.rows if self.t_begin is None or (self.t_begin <= t <= (self.t_end or t) + 0.05)]
+        if not inside:                      # timed region shorter than one sampling period: nearest samples under load
+            inside = [r for _, r in self.rows[-3:]]
+        for r in inside:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
@@ -181,8 +191,14 @@ def reference_decoder_gpu(dev, cfg, abstract, glob, q_host, batch, o4d_value, o4
 
         with torch.no_grad(), loader.quiet():
             ref_out = torch.cat(pass_device())
-            err = float((o4d_out - ref_out).abs().max() / ref_out.abs().max())
-            del ref_out
+            row_err = (o4d_out - ref_out).abs().max(dim=1)[0] / ref_out.abs().max()
+            err = {'max': float(row_err.max()), 'p9999': float(torch.quantile(row_err[::8].float(), 0.9999)),
+                   'median': float(row_err.median()), 'rows_above_1e-3': int((row_err > 1e-3).sum()),
+                   'rows_above_1e-4': int((row_err > 1e-4).sum()), 'rows': int(row_err.numel()),
+                   'note': 'per-row max |o4d - reference| / max |reference|; the reference on the GPU computes kNN '
+                           'distances with its own rounding, so rows whose k-th / (k+1)-th neighbours are a near tie '
+                           'pick a different neighbour -- those rows carry the maximum'}
+            del ref_out, row_err
             for _ in range(warm - 1):
                 pass_device()
             times = []
@@ -207,7 +223,7 @@ def reference_decoder_gpu(dev, cfg, abstract, glob, q_host, batch, o4d_value, o4
                 'warmup_passes': warm, 'timed_passes': iters, 'statistic': 'median',
                 'with_per_batch_h2d_d2h': {'value': rate_host, 'ms_per_frame': _median(host_times), 'timed_passes': 5},
                 'o4d_over_torch_eager': o4d_value / rate,
-                'max_rel_err_o4d_vs_reference_all_queries': err,
+                'rel_err_o4d_vs_reference_all_queries': err,
                 'sample': 'all %d grid queries of the frame in mini-batches of %d: the unmodified reference module '
                           '(model/implicit.py LocalPclResnetFC, copy in oracle/_ref) as torch eager fp32 on the same '
                           'GPU, scene encoding resident' % (nq, batch)}
@@ -388,11 +404,17 @@ def carla_config3(dev, lib, batch, steps):
     peak, _ = measured_peak()
     sel = torch.linspace(0, nq - 1, 4096).long().to(dev)        # the golden subset of the reference (make_golden.py)
     gold = torch.from_numpy(z['out']).to(dev)
+    # abstract_levels=2 duplicates every level-2 position in level 1: exact distance ties, where the reference's topk
+    # choice is implementation-defined.  Compare on rows whose neighbour sets are unambiguous (as the tests do).
+    from tests.test_oracle import boundary_tie_free
+    ok = boundary_tie_free(torch.from_numpy(z['query'])[:, :3], torch.from_numpy(z['abstract'])[:, :3],
+                           [cfg['implicit_args']['num_local_features'], cfg['implicit_args']['cross_attn_neighbors']]).to(dev)
     return {'queries_per_s': nq / (ms / 1e3), 'ms_per_step': ms, 'queries_per_step': nq, 'm_abstract': int(abstract.shape[0]),
             'd_out': d_out, 'kernel_families': fam,
             'roofline': {'bound': 'tensor', 'kernel': top, 'achieved': fam[top]['tflops'], 'peak': peak, 'unit': 'TFLOP/s',
                          'frac': fam[top]['tflops'] / peak},
-            'max_rel_err_vs_reference_golden': float((out[sel] - gold).abs().max() / gold.abs().max())}
+            'max_rel_err_vs_reference_golden': float((out[sel][ok] - gold[ok]).abs().max() / gold[ok].abs().max()),
+            'golden_rows_compared': int(ok.sum()), 'golden_rows_with_exact_distance_ties': int((~ok).sum())}
 
 
 def strong_scaling(dev, world, rank, enc, dec, pcl, cfg, frames=2):
@@ -672,12 +694,13 @@ def run_o4d(args):
             if world > 1 and comm:
                 dist.all_gather_into_tensor(gathered, out_dev)
 
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()                  # nvidia-smi needs a few hundred ms to start: launch it before the warm-up
         for _ in range(args.warmup):
             step_device()
-        sampler = ClockSampler(local)
         barrier()
-        if rank == 0:
-            sampler.start()
+        sampler.mark_begin()
         launches0 = lib.o4d_launch_count()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record()
@@ -685,6 +708,7 @@ def run_o4d(args):
             step_device()
         t1.record()
         barrier()
+        sampler.mark_end()
         launches = lib.o4d_launch_count() - launches0
         clocks = sampler.stop() if rank == 0 else None
         ms = max_over_ranks(t0.elapsed_time(t1))

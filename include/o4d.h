@@ -142,6 +142,21 @@ int o4d_pt_layer_forward(const float* const* p,
                          float* out, int64_t* knn_idx_out,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------ fused residual block
+ * ResnetBlockFC.forward, model/implicit.py:93-101 (ReLU, d_in == d_out so no shortcut layer):
+ *     out = x + fc_1( relu( fc_0( relu(x) ) ) )
+ * as ONE launch of the fused multi-layer kernel (csrc/mlp_chain.cu): the hidden activation never exists as fp32
+ * in memory, both contractions run on tcgen05 (precision 1 = bf16x3, fp32-grade; 2 = single bf16 pass).
+ * x (rows, d) ldx;  w0 (d_hidden, d), b0 (d_hidden) | NULL;  w1 (d, d_hidden), b1 (d) | NULL;  out (rows, d) ldo.
+ * d and d_hidden must be multiples of 32 (else O4D_E_UNSUPPORTED: compose two o4d_linear_f32 calls); rows and
+ * biases 16-byte aligned.  out must not alias x.  workspace: o4d_resblock_workspace_bytes (0 = unsupported shape). */
+size_t o4d_resblock_workspace_bytes(int64_t rows, int d, int d_hidden);
+int o4d_resblock_forward_f32(const float* x, int64_t rows, int d, int64_t ldx,
+                             const float* w0, const float* b0, int d_hidden,
+                             const float* w1, const float* b1,
+                             float* out, int64_t ldo, int precision,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------ down transition
  * DownTransition.forward, model/modules.py:113-163, one cloud:
  *   idx = sort(fps(pos, ceil(n/factor)));  nbr = knn(pos[idx] -> pos, k)

@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fused_kernel(const Params p) 
         }
         const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         // ---- gather staging (see G_PITCH): this warp copies 16 Ka rows and up to 2 Qa rows per chunk
-        asm volatile("bar.sync 1, 256;" ::: "memory");                 // s_j complete
+        __syncwarp(); asm volatile("bar.sync 1, 256;" ::: "memory");                 // s_j complete
         const int g_piece = lane & 7, g_sub = lane >> 3;
         const int g_rbase = (warp & 3) * 32 + (warp >> 2) * 16;
         int gj[4];
@@ -440,7 +440,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fused_kernel(const Params p) 
                            p.vtab + (int64_t)gj[it] * d + cc * 32 + g_piece * 4);
         };
         // every warp has consumed the last Ka/Qa stage (its G_EMPTY arrival precedes this barrier)
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        __syncwarp(); asm volatile("bar.sync 1, 256;" ::: "memory");
         issue_v(0, 0);
         if (ND > 1) issue_v(1, 1);
         cp_async_commit();
@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fused_kernel(const Params p) 
             const int gn = min(GROUP, ND - g0);
             if (dbg) t0 = clock64();
             cp_async_wait_all();
-            asm volatile("bar.sync 2, 288;" ::: "memory");         // V slices landed; previous group's tiles are free
+            __syncwarp(); asm volatile("bar.sync 2, 288;" ::: "memory");         // V slices landed; previous group's tiles are free
             if (dbg) t_bar += clock64() - t0;
 #pragma unroll
             for (int u = 0; u < GROUP; ++u) {
@@ -491,7 +491,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fused_kernel(const Params p) 
                 if (dbg) t_stage += clock64() - t0;
             }
             if (dbg) t0 = clock64();
-            asm volatile("bar.sync 2, 288;" ::: "memory");         // the group's tiles are complete, V stages consumed
+            __syncwarp(); asm volatile("bar.sync 2, 288;" ::: "memory");         // the group's tiles are complete, V stages consumed
             if (dbg) { const long long t1 = clock64(); t_bar += t1 - t0; t0 = t1; }
             if (g0 + GROUP < ND) {                                  // next group's V slices: in flight during the reduce
                 issue_v(g0 + GROUP, 0);
@@ -544,8 +544,8 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fused_kernel(const Params p) 
         const int64_t q0 = (int64_t)blockIdx.x * p.tq;
         for (int g0 = 0; g0 < ND; g0 += EPI_GROUP) {
             const int gn = min(EPI_GROUP, ND - g0);
-            asm volatile("bar.sync 2, 288;" ::: "memory");
-            asm volatile("bar.sync 2, 288;" ::: "memory");         // the group's tiles are complete
+            __syncwarp(); asm volatile("bar.sync 2, 288;" ::: "memory");
+            __syncwarp(); asm volatile("bar.sync 2, 288;" ::: "memory");         // the group's tiles are complete
             const int ntask = gn * p.tq;
             for (int task = ROW_WARPS; task < ntask; task += EPI_WARPS) {
                 const int u = task >= p.tq ? 1 : 0, q = task - u * p.tq;

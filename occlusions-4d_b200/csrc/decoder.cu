@@ -7,6 +7,8 @@
 // global half of every lin_z (implicit.py:417: lin_z(cat[global, local]) =
 // W[:, :Dg] g + b  +  W[:, Dg:] f_local; the first term is a per-scene vector).
 #include "o4d_common.cuh"
+#include "mlp_chain.cuh"
+#include <stdlib.h>
 
 namespace o4d {
 
@@ -243,7 +245,28 @@ struct DecWs {
     float *dist_l, *f_loc, *pe, *x, *h, *y;
     char* sub;
     size_t sub_bytes, bytes;
+    // activation images of the fused multi-layer path (mlp_chain.cu); null when that path cannot run
+    uint8_t *img_pe, *img_floc, *img_x, *img_h, *img_y;
 };
+
+// The fused multi-layer MLP path (mlp_chain.cu) needs: tcgen05 precision, lin_z folded (packed K-concatenated
+// weights), widths in whole 32-column image chunks, every layer inside the chain kernel's tile limits, and -- when
+// there are cross-attention layers -- the fused attention kernel (it takes Qa and leaves the aggregate as fp32).
+// O4D_MLP_CHAIN=0 forces the per-layer kernels (A/B timing).
+static bool dec_chain_possible(const o4d_decoder_config* c) {
+    static int env = -1;
+    if (env < 0) {
+        const char* e = getenv("O4D_MLP_CHAIN");
+        env = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (!env || c->precision == 0) return false;
+    const int H = c->d_hidden, E = c->d_latent_local;
+    const int in_w = c->pos_encoding_freqs > 0 ? c->d_in * (2 * c->pos_encoding_freqs + 1) : c->d_in;
+    if (H % 32 != 0 || H < 32) return false;
+    if (c->cross_attn_layers > 0 && !attn_fused_supported(H, c->cross_attn_neighbors)) return false;
+    return mlp_chain_layer_ok(H, H) && mlp_chain_layer_ok(H, 2 * H) && mlp_chain_layer_ok(H, c->d_out) &&
+           mlp_chain_layer_ok((in_w + 31) / 32 * 32 + E, H) && mlp_chain_layer_ok(H + E, H);
+}
 
 static DecWs dec_ws(const o4d_decoder_config* c, int64_t nq, void* base, size_t cap) {
     Arena a(base, cap);
@@ -260,9 +283,128 @@ static DecWs dec_ws(const o4d_decoder_config* c, int64_t nq, void* base, size_t 
     w.y = a.get<float>((size_t)nq * H);
     w.sub_bytes = c->cross_attn_layers > 0 ? attn_core_workspace_bytes(nq, H, c->cross_attn_neighbors) : 0;
     w.sub = a.get<char>(w.sub_bytes);
+    w.img_pe = w.img_floc = w.img_x = w.img_h = w.img_y = nullptr;
+    if (dec_chain_possible(c)) {
+        const int in_w = c->pos_encoding_freqs > 0 ? pe_w : c->d_in;
+        w.img_pe = a.get<uint8_t>(act_image_bytes(nq, in_w));
+        w.img_floc = a.get<uint8_t>(act_image_bytes(nq, c->d_latent_local));
+        w.img_x = a.get<uint8_t>(act_image_bytes(nq, H));
+        w.img_h = a.get<uint8_t>(act_image_bytes(nq, H));
+        w.img_y = a.get<uint8_t>(act_image_bytes(nq, H));
+    }
     w.bytes = a.off;
     if (!a.ok) w.x = nullptr;
     return w;
+}
+
+// ---- fused multi-layer path --------------------------------------------------------------------------------------
+// The whole dense part of do_forward_attention (implicit.py:403-443) as at most cross_attn_layers + 1 launches of the
+// chain kernel (mlp_chain.cu), cut only where a cross-attention layer needs every query's Qa:
+//   [lin_in + lin_z0] -> { fc_0 -> fc_1 (+ lin_z of the next block) }* -> Qa      | fused attention |
+//   [layer3 + lin_z]  -> { ... }* -> Qa                                            | fused attention |
+//   [layer3 + lin_z]  -> { ... }* -> lin_out
+// Layer inputs / outputs between the launches' layers are activation images; x (the residual stream, fp32) is the
+// only full-width fp32 tensor left besides Qa and the attention aggregate.
+struct ChainBuild {
+    mc::Program prog;
+    cudaStream_t st;
+    int rc = 0;
+    ChainBuild(int64_t rows, int split, cudaStream_t s) : st(s) {
+        prog.nops = 0;
+        prog.rows = rows;
+        prog.split = split;
+        prog.tiles = 0;
+    }
+    void flush() {
+        if (rc == 0 && prog.nops > 0) rc = mlp_chain_launch(prog, st);
+        prog.nops = 0;
+    }
+    // Y = [A1 | A2] W^T + bias (+ res) -> fp32 `out` and / or image `img`
+    void add(const PackedSet& ps, const uint8_t* a1, int k1, const uint8_t* a2, int k2, const float* wkey, int n,
+             const float* bias, float* out, int64_t ldo, const float* res, int64_t ldr, uint8_t* img, int img_relu) {
+        if (rc != 0) return;
+        if (prog.nops == mc::MAX_OPS) flush();
+        const void* packed = ps.find(wkey);
+        if (!packed) {
+            set_error("decoder: missing packed weight for the fused MLP path");
+            rc = O4D_E_ARG;
+            return;
+        }
+        mc::Op& op = prog.op[prog.nops++];
+        op.a1 = a1;
+        op.k1c = (k1 + 31) / 32;
+        op.a2 = a2;
+        op.k2c = a2 ? (k2 + 31) / 32 : 0;
+        op.w = (const uint8_t*)packed;
+        op.bias = bias;
+        op.out = out;
+        op.ldo = ldo;
+        op.res = res;
+        op.ldr = ldr;
+        op.img = img;
+        op.img_cpt = (n + 31) / 32;
+        op.img_relu = img_relu;
+        op.n_img = 0;
+        op.n = n;
+        mlp_chain_tiling(n, &op.bn, &op.ntiles);
+        op.k_alg = (double)k1 + (a2 ? k2 : 0);
+    }
+};
+
+static int decoder_forward_chain(const o4d_decoder_config* c, const DecParams& d, const SceneView& s, const PackedSet& ps,
+                                 const DecWs& w, int64_t m, const float* query, const float* in_ptr, int in_w, int64_t nq,
+                                 float* out, float* penult, cudaStream_t st) {
+    const int H = c->d_hidden, E = c->d_latent_local;
+    O4D_TRY(act_image_launch(in_ptr, in_w, nq, in_w, 0, w.img_pe, st));
+    O4D_TRY(act_image_launch(w.f_loc, E, nq, E, 0, w.img_floc, st));
+    float* qa = (float*)w.sub;                        // (nq, 2H): first carve of the attention workspace
+    ChainBuild cb(nq, c->precision == 1 ? 1 : 0, st);
+    // implicit.py:403-408 + :416-418 of block 0:  x = lin_in(pe) + lin_z[0](f_query)
+    cb.add(ps, w.img_pe, in_w, w.img_floc, E, s.wcat[0], H, s.bcat[0], w.x, H, nullptr, 0, w.img_x, 1);
+    for (int b = 0; b < c->n_blocks; ++b) {
+        const bool has_next = b + 1 < c->n_blocks;
+        // implicit.py:93  h = fc_0(relu(x)): only the image of relu(h) is produced
+        cb.add(ps, w.img_x, H, nullptr, 0, d.fc0_w[b], H, d.fc0_b[b], nullptr, 0, nullptr, 0, w.img_h, 1);
+        if (d.use_pt[b] < 0) {
+            // implicit.py:94-101 (+ :416-418 of block b + 1)  x += fc_1(relu(h)) [+ lin_z[b+1](f_query)]
+            if (has_next)
+                cb.add(ps, w.img_h, H, w.img_floc, E, s.wcat[b + 1], H, s.bcat[b + 1], w.x, H, w.x, H, w.img_x, 1);
+            else
+                cb.add(ps, w.img_h, H, nullptr, 0, d.fc1_w[b], H, d.fc1_b[b], w.x, H, w.x, H, w.img_x, 1);
+            continue;
+        }
+        // block followed by a cross-attention layer (implicit.py:421-439 -> modules.py:61-65)
+        const int j = d.use_pt[b];
+        PtBlockParams pp = PtBlockParams::from(d.pt[j]);
+        cb.add(ps, w.img_h, H, nullptr, 0, d.fc1_w[b], H, d.fc1_b[b], w.x, H, w.x, H, w.img_x, 0);   // raw x image for Qa
+        // Qa = (W_a1 W_q W_1) x + (W_a1 W_q b_1 + cvec)
+        cb.add(ps, w.img_x, H, nullptr, 0, s.wqa[j], 2 * H, s.bqa[j], qa, 2 * H, nullptr, 0, nullptr, 0);
+        cb.flush();
+        O4D_TRY(cb.rc);
+        AttnTables T;
+        {
+            Arena ta(s.tables[j], s.tables_bytes);   // same carve-up as attn_tables_launch
+            T.ka = ta.get<float>((size_t)m * 2 * H);
+            T.wc = ta.get<float>((size_t)2 * H * 32);
+            T.cvec = ta.get<float>((size_t)2 * H);
+            T.vtab = s.vtab[j];
+            T.fused = s.fused[j];
+        }
+        O4D_TRY(attn_fused_launch(pp, T, qa, query, c->d_in, s.abs_xyz, 3, w.idx_c, nq, H, c->cross_attn_neighbors, w.y,
+                                  c->precision, st));
+        O4D_TRY(act_image_launch(w.y, H, nq, H, 0, w.img_y, st));
+        // modules.py:64-65  x += layer3(agg) [+ lin_z[b+1](f_query)]
+        if (has_next)
+            cb.add(ps, w.img_y, H, w.img_floc, E, s.wcat[b + 1], H, s.bcat[b + 1], w.x, H, w.x, H, w.img_x, 1);
+        else
+            cb.add(ps, w.img_y, H, nullptr, 0, pp.w3, H, pp.b3, w.x, H, w.x, H, w.img_x, 1);
+    }
+    // implicit.py:441-443  out = lin_out(relu(x))
+    cb.add(ps, w.img_x, H, nullptr, 0, d.lin_out_w, c->d_out, d.lin_out_b, out, c->d_out, nullptr, 0, nullptr, 0);
+    cb.flush();
+    O4D_TRY(cb.rc);
+    if (penult) O4D_TRY(copy2d_launch(w.x, H, nq, H, penult, H, st));           // implicit.py:441
+    return 0;
 }
 
 int decoder_forward(const o4d_decoder_config* c, const float* const* P, const void* scene, int64_t m,
@@ -304,6 +446,8 @@ int decoder_forward(const o4d_decoder_config* c, const float* const* P, const vo
     const float* in_ptr = c->pos_encoding_freqs > 0 ? w.pe : query;
     const int in_w = c->pos_encoding_freqs > 0 ? pe_w : c->d_in;
     if (c->pos_encoding_freqs > 0) O4D_TRY(posenc_launch(query, nq, c->d_in, c->pos_encoding_freqs, w.pe, st));
+    if (fold && w.img_x && tc_shape_ok(nq, H, c->d_out))
+        return decoder_forward_chain(c, d, s, ps, w, m, query, in_ptr, in_w, nq, out, penult, st);
     if (fold)
         O4D_TRY(linear_ps_launch(&ps, in_ptr, nq, in_w, in_w, s.wcat[0], s.kcat[0], s.bcat[0], H, nullptr, 0, w.x, H, 0,
                                  prec, st, &cat));

@@ -1,0 +1,527 @@
+// Fused multi-layer MLP kernel of the implicit decoder ("chain"): ONE persistent launch runs a whole
+// sequence of dense layers -- lin_in, every ResnetBlockFC (fc_0 -> ReLU -> fc_1 + residual), the lin_z
+// additions folded into the producing layers, the composite Qa projection of the next cross-attention block,
+// lin_out -- for every 128-row tile of queries (model/implicit.py:93-101, 403-418, 441-443).  All of these
+// are row-local, so a CTA carries ITS row tiles through the whole sequence without any grid-wide barrier.
+//
+// What moved compared with the per-layer kernel (gemm_tc.cu), and why:
+//   * Activations between layers are exchanged as "activation images": per (128-row tile, 32-column chunk) one
+//     16 KB block [bf16 hi 8 KB][bf16 lo 8 KB], each [k/8][row/8][8 rows][8 values] -- byte for byte the K-major
+//     no-swizzle core-matrix layout the UMMA descriptor of the A operand describes.  The epilogue of the
+//     producing layer writes them (ReLU and the hi/lo split applied once, by the producer); the consuming layer's
+//     A operand is then ONE cp.async.bulk per K chunk issued by one thread.  The old main loop had eight producer
+//     warps doing LDG fp32 -> split -> STS for every chunk of every n-tile and was bound by outstanding L1 sector
+//     requests (36 k -> 27 k cycles per tile with full-sector loads, 15 k without the loads).
+//   * The hidden activations h of a residual block never exist as fp32 anywhere: fc_0's epilogue emits only the
+//     image of relu(h).  The residual stream x stays fp32 in HBM (it is the `penult` output and the exact
+//     residual operand) next to its image.
+//   * One CTA per SM, roles by warp: warp 8 streams A-image chunks and packed weight slabs (TMA engine), warp 9
+//     issues tcgen05.mma, warps 0-7 run epilogues.  Two TMEM accumulators (columns 0 and 256): the epilogue of
+//     item i overlaps the main loop of item i + 1.  An item is (layer, row tile, n-tile); a CTA interleaves its
+//     row tiles inside a layer, so the layer-to-layer dependency of a tile (its images must be complete before the
+//     next layer loads them) is normally satisfied two items earlier and costs nothing.
+//   * bf16x3 (hi*hi + lo*hi + hi*lo, fp32 accumulate) as everywhere else; `split` = 0 issues hi*hi only.
+#include "o4d_common.cuh"
+#include "tc_helpers.cuh"
+#include "mlp_chain.cuh"
+
+namespace o4d {
+namespace mc {
+
+using namespace tch;
+
+constexpr int BK = 32;
+constexpr int STAGES = 4;
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = (EPI_WARPS + 2) * 32;
+constexpr int A_HALF = BM * BK * 2;                      // 8 KB: one bf16 image half of a chunk
+constexpr int W_BYTES_MAX = 2 * BN_MAX * BK * 2;         // hi + lo slab of a 208-column n-tile
+constexpr int STAGE_BYTES = IMG_CHUNK_BYTES + W_BYTES_MAX;
+constexpr int SLD = 36;                                  // epilogue staging row pitch (floats)
+constexpr int STG_BYTES = EPI_WARPS * 32 * SLD * 4;
+constexpr int OFF_STG = STAGES * STAGE_BYTES;
+constexpr int OFF_BAR = OFF_STG + STG_BYTES;
+constexpr int SMEM_BYTES = OFF_BAR + 256;
+static_assert(IMG_CHUNK_BYTES == 2 * A_HALF, "image chunk = hi + lo halves");
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+
+__device__ __forceinline__ void st_release_shared(uint32_t addr, int v) {
+    asm volatile("st.release.cta.shared::cta.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_shared(uint32_t addr) {
+    int v;
+    asm volatile("ld.acquire.cta.shared::cta.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// byte offset of element (tile-row trow, column gc) inside an image with `cpt` chunks per tile (hi half)
+__device__ __forceinline__ size_t img_off(int64_t tile, int cpt, int trow, int gc) {
+    return ((size_t)tile * cpt + (gc >> 5)) * IMG_CHUNK_BYTES + (size_t)(((gc & 31) >> 3) * (BM * 16) + (trow >> 3) * 128 +
+                                                                          (trow & 7) * 16 + (gc & 7) * 2);
+}
+
+__device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
+    return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+__global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const Program P) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+    // full[4], empty[4], acc_full[2], acc_empty[2]; then the TMEM slot and the per-warp progress counters
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    int* done = reinterpret_cast<int*>(bars + 13);       // [EPI_WARPS] items finished by each epilogue warp
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]);
+    const uint32_t accf0 = smem_u32(&bars[2 * STAGES]), acce0 = smem_u32(&bars[2 * STAGES + 2]);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t done0 = smem_u32(done);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full0 + 8 * s, 1);                // the producer's arrive.expect_tx (+ the copies' bytes)
+            mbar_init(empty0 + 8 * s, 1);               // one tcgen05.commit
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(accf0 + 8 * a, 1);                // one tcgen05.commit
+            mbar_init(acce0 + 8 * a, EPI_WARPS);        // every epilogue warp has drained the accumulator
+        }
+        for (int w = 0; w < EPI_WARPS; ++w) done[w] = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == EPI_WARPS + 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    // row tiles of this CTA: blockIdx.x, + gridDim.x, ...
+    const int ntl = (P.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (warp < EPI_WARPS) {
+        // ================================================================== epilogue warps
+        const int quarter = warp & 3, chalf = warp >> 2;
+        const uint32_t taddr_q = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        float* stg = reinterpret_cast<float*>(smem + OFF_STG) + warp * (32 * SLD);
+        int item = 0;
+        for (int o = 0; o < P.nops; ++o) {
+            const Op& op = P.op[o];
+            const int bn = op.bn;
+            const bool relu_img = op.img_relu != 0;
+            const int nblk = (bn + 31) / 32;
+            const int c_begin = chalf ? ((nblk + 1) / 2) * 32 : 0;
+            const int c_end = chalf ? bn : min(bn, ((nblk + 1) / 2) * 32);
+            const bool image_only = op.out == nullptr && op.res == nullptr;
+            const bool vec_ok = (op.n % 4 == 0) && (!op.out || ((op.ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(op.out) & 15) == 0))) &&
+                                (!op.res || ((op.ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(op.res) & 15) == 0))) &&
+                                (!op.bias || ((reinterpret_cast<uintptr_t>(op.bias) & 15) == 0));
+            for (int j = 0; j < ntl; ++j) {
+                const int64_t tile = (int64_t)blockIdx.x + (int64_t)j * gridDim.x;
+                const int64_t row0 = tile * BM + quarter * 32;          // first row of this warp
+                const int rows_here = (int)max((int64_t)0, min((int64_t)32, P.rows - row0));
+                for (int nh = 0; nh < op.ntiles; ++nh, ++item) {
+                    const int acc = item & 1;
+                    mbar_wait(accf0 + 8 * acc, (uint32_t)(item >> 1) & 1u);
+                    tc_fence_after();
+                    const uint32_t taddr = taddr_q + (uint32_t)(acc * 256);
+                    const int col_base = nh * bn;
+                    if (image_only) {
+                        // ---- (E1) row per thread: + bias, ReLU, split, two 16-byte lines per 8 columns.  A warp
+                        // instruction stores 32 rows x 16 B = 512 contiguous bytes of the image.
+                        const int trow = quarter * 32 + lane;
+                        for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+                            float v[16];
+                            tmem_ld16(taddr + (uint32_t)c0, v);
+                            const int gc0 = col_base + c0;
+#pragma unroll
+                            for (int h8 = 0; h8 < 2; ++h8) {
+                                const int gc = gc0 + h8 * 8;
+                                if (gc >= op.n) continue;               // n % 32 == 0 for image outputs: whole groups only
+                                float b8[8];
+                                if (op.bias) {
+                                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(op.bias + gc));
+                                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(op.bias + gc + 4));
+                                    b8[0] = b0.x; b8[1] = b0.y; b8[2] = b0.z; b8[3] = b0.w;
+                                    b8[4] = b1.x; b8[5] = b1.y; b8[6] = b1.z; b8[7] = b1.w;
+                                } else {
+#pragma unroll
+                                    for (int e = 0; e < 8; ++e) b8[e] = 0.f;
+                                }
+                                uint32_t hi[4], lo[4];
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    float x0 = v[h8 * 8 + 2 * e] + b8[2 * e], x1 = v[h8 * 8 + 2 * e + 1] + b8[2 * e + 1];
+                                    if (relu_img) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+                                    __nv_bfloat16 h0, l0, h1, l1;
+                                    split_bf16(x0, h0, l0);
+                                    split_bf16(x1, h1, l1);
+                                    hi[e] = pack2(h0, h1);
+                                    lo[e] = pack2(l0, l1);
+                                }
+                                uint8_t* dst = op.img + img_off(tile, op.img_cpt, trow, gc);
+                                *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                                *reinterpret_cast<uint4*>(dst + A_HALF) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                            }
+                        }
+                    } else if (vec_ok) {
+                        // ---- (E2) fp32 output and / or residual: 32 x 32 blocks transposed through a padded staging
+                        // tile so that residual loads and output stores are contiguous 128-byte row segments; the
+                        // image (if any) is written from the same mapping: 4 columns = half a core-matrix line.
+                        const int rr = lane >> 3, c4 = (lane & 7) * 4;
+                        float4 resn[8];
+                        auto load_res = [&](int c0) {
+                            const int gc = col_base + c0 + c4;
+                            const bool ok = op.res && c4 < min(32, bn - c0) && gc < op.n;
+#pragma unroll
+                            for (int it = 0; it < 8; ++it) {
+                                const int row = it * 4 + rr;
+                                resn[it] = (ok && row < rows_here) ? *reinterpret_cast<const float4*>(op.res + (row0 + row) * op.ldr + gc)
+                                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+                            }
+                        };
+                        if (c_begin < c_end) load_res(c_begin);
+                        for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+                            const int width = min(32, bn - c0);
+                            float4 res[8];
+#pragma unroll
+                            for (int it = 0; it < 8; ++it) res[it] = resn[it];
+                            if (c0 + 32 < c_end) load_res(c0 + 32);
+                            float v[32];
+                            tmem_ld16(taddr + (uint32_t)c0, v);
+                            if (width > 16) tmem_ld16(taddr + (uint32_t)(c0 + 16), v + 16);
+#pragma unroll
+                            for (int i = 0; i < 32; i += 4)
+                                if (i < width) *reinterpret_cast<float4*>(stg + lane * SLD + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                            __syncwarp();
+                            const int gc = col_base + c0 + c4;
+                            if (c4 < width && gc < op.n) {
+                                const float4 bv = op.bias ? *reinterpret_cast<const float4*>(op.bias + gc) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                                for (int it = 0; it < 8; ++it) {
+                                    const int row = it * 4 + rr;
+                                    float4 x = *reinterpret_cast<const float4*>(stg + row * SLD + c4);
+                                    x.x += bv.x + res[it].x; x.y += bv.y + res[it].y; x.z += bv.z + res[it].z; x.w += bv.w + res[it].w;
+                                    if (op.out && row < rows_here) *reinterpret_cast<float4*>(op.out + (row0 + row) * op.ldo + gc) = x;
+                                    if (op.img) {
+                                        if (relu_img) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+                                        __nv_bfloat16 h0, l0, h1, l1, h2, l2, h3, l3;
+                                        split_bf16(x.x, h0, l0); split_bf16(x.y, h1, l1);
+                                        split_bf16(x.z, h2, l2); split_bf16(x.w, h3, l3);
+                                        uint8_t* dst = op.img + img_off(tile, op.img_cpt, quarter * 32 + row, gc);
+                                        *reinterpret_cast<uint2*>(dst) = make_uint2(pack2(h0, h1), pack2(h2, h3));
+                                        *reinterpret_cast<uint2*>(dst + A_HALF) = make_uint2(pack2(l0, l1), pack2(l2, l3));
+                                    }
+                                }
+                            }
+                            __syncwarp();
+                        }
+                    } else {
+                        // ---- (E3) narrow / unaligned fp32 outputs (lin_out: 9 .. 33 columns): one row per thread
+                        const int64_t grow = row0 + lane;
+                        for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+                            float v[16];
+                            tmem_ld16(taddr + (uint32_t)c0, v);
+                            if (lane < rows_here && op.out) {
+                                const int gc0 = col_base + c0;
+                                for (int i = 0; i < 16 && gc0 + i < op.n; ++i) {
+                                    float x = v[i] + (op.bias ? op.bias[gc0 + i] : 0.f);
+                                    if (op.res) x += op.res[grow * op.ldr + gc0 + i];
+                                    op.out[grow * op.ldo + gc0 + i] = x;
+                                }
+                            }
+                        }
+                    }
+                    // accumulator drained -> the MMA issuer may overwrite it (item + 2)
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acce0 + 8 * acc);
+                    // this warp's part of the item is in global memory: make it visible to the TMA engine (async
+                    // proxy) of this CTA before the producer is told (generic stores -> fence -> flag)
+                    __threadfence();
+                    fence_proxy_async_all();
+                    __syncwarp();
+                    if (lane == 0) st_release_shared(done0 + 4 * warp, item + 1);
+                }
+            }
+        }
+    } else if (warp == EPI_WARPS) {
+        // ================================================================== producer: A-image chunks + weight slabs
+        if (lane == 0) {
+            int g = 0;            // running stage counter
+            int items_before = 0; // items of all earlier ops
+            int prev_nt = 0;      // n-tiles per row tile of the previous op
+            for (int o = 0; o < P.nops; ++o) {
+                const Op& op = P.op[o];
+                const uint32_t w_bytes = (uint32_t)(2 * op.bn * BK * 2);
+                const int nch = op.k1c + op.k2c;
+                for (int j = 0; j < ntl; ++j) {
+                    const int64_t tile = (int64_t)blockIdx.x + (int64_t)j * gridDim.x;
+                    if (o > 0) {
+                        // the images this op reads were written by the previous op's epilogues of THIS tile: wait
+                        // until every epilogue warp has finished its last item of (o - 1, j)
+                        const int need = items_before - (ntl - 1 - j) * prev_nt;
+                        for (int w = 0; w < EPI_WARPS; ++w) {
+                            if (ld_acquire_shared(done0 + 4 * w) >= need) continue;
+                            const long long t0 = clock64();
+                            while (ld_acquire_shared(done0 + 4 * w) < need) {
+                                __nanosleep(64);
+                                if (clock64() - t0 > 4000000000LL) __trap();
+                            }
+                        }
+                        fence_proxy_async_all();
+                    }
+                    const uint8_t* a1 = op.a1 + (size_t)tile * op.k1c * IMG_CHUNK_BYTES;
+                    const uint8_t* a2 = op.a2 ? op.a2 + (size_t)tile * op.k2c * IMG_CHUNK_BYTES : nullptr;
+                    for (int nh = 0; nh < op.ntiles; ++nh) {
+                        const uint8_t* wsrc = op.w + (size_t)nh * nch * w_bytes;
+                        for (int c = 0; c < nch; ++c, ++g) {
+                            const int s = g % STAGES;
+                            const uint32_t ph = (uint32_t)(g / STAGES) & 1u;
+                            mbar_wait(empty0 + 8 * s, ph ^ 1u);
+                            const uint32_t dst = smem_base + s * STAGE_BYTES;
+                            mbar_arrive_expect_tx(full0 + 8 * s, IMG_CHUNK_BYTES + w_bytes);
+                            const uint8_t* asrc = c < op.k1c ? a1 + (size_t)c * IMG_CHUNK_BYTES : a2 + (size_t)(c - op.k1c) * IMG_CHUNK_BYTES;
+                            bulk_g2s(dst, asrc, IMG_CHUNK_BYTES, full0 + 8 * s);
+                            bulk_g2s(dst + IMG_CHUNK_BYTES, wsrc + (size_t)c * w_bytes, w_bytes, full0 + 8 * s);
+                        }
+                    }
+                }
+                items_before += ntl * op.ntiles;
+                prev_nt = op.ntiles;
+            }
+        }
+    } else {
+        // ================================================================== MMA issuer
+        if (lane == 0) {
+            int g = 0, item = 0;
+            const uint32_t lbo_a = BM * 16;
+            for (int o = 0; o < P.nops; ++o) {
+                const Op& op = P.op[o];
+                const int bn = op.bn;
+                const uint32_t idesc = umma_idesc(bn);
+                const uint32_t lbo_b = (uint32_t)bn * 16;
+                const uint32_t b_half = (uint32_t)bn * BK * 2;
+                const int nch = op.k1c + op.k2c;
+                for (int j = 0; j < ntl; ++j) {
+                    for (int nh = 0; nh < op.ntiles; ++nh, ++item) {
+                        const int acc = item & 1;
+                        // accumulator free?  (its previous user was item - 2)
+                        mbar_wait(acce0 + 8 * acc, ((uint32_t)(item >> 1) & 1u) ^ 1u);
+                        tc_fence_after();
+                        const uint32_t dcol = tmem_base + (uint32_t)(acc * 256);
+                        for (int c = 0; c < nch; ++c, ++g) {
+                            const int s = g % STAGES;
+                            const uint32_t ph = (uint32_t)(g / STAGES) & 1u;
+                            mbar_wait(full0 + 8 * s, ph);
+                            tc_fence_after();
+                            const uint32_t a_hi = smem_base + s * STAGE_BYTES;
+                            const uint32_t a_lo = a_hi + A_HALF;
+                            const uint32_t b_hi = a_hi + IMG_CHUNK_BYTES;
+                            const uint32_t b_lo = b_hi + b_half;
+#pragma unroll
+                            for (int ks = 0; ks < BK / 16; ++ks) {
+                                const uint64_t da_hi = umma_desc(a_hi + ks * 2 * lbo_a, lbo_a, 128);
+                                const uint64_t db_hi = umma_desc(b_hi + ks * 2 * lbo_b, lbo_b, 128);
+                                umma_f16(dcol, da_hi, db_hi, idesc, (c | ks) ? 1u : 0u);
+                                if (P.split) {
+                                    const uint64_t da_lo = umma_desc(a_lo + ks * 2 * lbo_a, lbo_a, 128);
+                                    const uint64_t db_lo = umma_desc(b_lo + ks * 2 * lbo_b, lbo_b, 128);
+                                    umma_f16(dcol, da_lo, db_hi, idesc, 1u);
+                                    umma_f16(dcol, da_hi, db_lo, idesc, 1u);
+                                }
+                            }
+                            umma_commit(empty0 + 8 * s);          // frees the stage when these MMAs retire
+                        }
+                        umma_commit(accf0 + 8 * acc);             // accumulator complete -> epilogue
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == EPI_WARPS + 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// fp32 (rows, cols) row-major -> activation image with ceil(cols / 32) chunks per tile; padding rows / columns = 0.
+// thread = (row, 8-column group): 4 consecutive lanes read one 128-byte line of a row, and the 8 rows of a warp
+// write 128 contiguous bytes per core-matrix column group.
+__global__ void image_from_f32_kernel(const float* __restrict__ src, int64_t ld, int64_t rows, int cols, int relu,
+                                      uint8_t* __restrict__ img, int cpt, int64_t tiles) {
+    const int64_t units = tiles * cpt * (BM * 4);          // (tile, chunk, row, kc)
+    for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < units; u += (int64_t)gridDim.x * blockDim.x) {
+        const int kc = (int)(u & 3);
+        const int trow = (int)((u >> 2) % BM);
+        const int64_t tc = u / (BM * 4);
+        const int chunk = (int)(tc % cpt);
+        const int64_t tile = tc / cpt;
+        const int64_t grow = tile * BM + trow;
+        const int gc = chunk * 32 + kc * 8;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = 0.f;
+        if (grow < rows) {
+            const float* p = src + grow * ld + gc;
+            if (gc + 8 <= cols && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+                const float4 a = *reinterpret_cast<const float4*>(p);
+                const float4 b = *reinterpret_cast<const float4*>(p + 4);
+                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    if (gc + e < cols) v[e] = p[e];
+            }
+        }
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float x0 = v[2 * e], x1 = v[2 * e + 1];
+            if (relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+            __nv_bfloat16 h0, l0, h1, l1;
+            split_bf16(x0, h0, l0);
+            split_bf16(x1, h1, l1);
+            hi[e] = pack2(h0, h1);
+            lo[e] = pack2(l0, l1);
+        }
+        uint8_t* dst = img + img_off(tile, cpt, trow, gc);
+        *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(dst + A_HALF) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+}  // namespace mc
+
+size_t act_image_bytes(int64_t rows, int cols) {
+    return (size_t)cdiv(rows, mc::BM) * (size_t)cdiv(cols, 32) * mc::IMG_CHUNK_BYTES;
+}
+
+int act_image_launch(const float* src, int64_t ld, int64_t rows, int cols, int relu, void* img, cudaStream_t st) {
+    if (rows <= 0) return 0;
+    const int64_t tiles = cdiv(rows, mc::BM);
+    const int cpt = (int)cdiv(cols, 32);
+    const int64_t units = tiles * cpt * (mc::BM * 4);
+    int64_t blocks = cdiv(units, 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    ProfScope prof(PROF_MISC, 0.0, st);
+    mc::image_from_f32_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, ld, rows, cols, relu, (uint8_t*)img, cpt, tiles);
+    O4D_LAUNCH_CHECK();
+    return 0;
+}
+
+// tc::pack_meta's tiling (gemm_tc.cu): the packed weights are shared with the per-layer kernel
+void mlp_chain_tiling(int64_t n, int* bn_out, int* ntiles_out) {
+    const int tiles = (int)cdiv(n, 256);
+    int bn = (int)cdiv(n, tiles);
+    bn = (bn + 15) / 16 * 16;
+    *bn_out = bn;
+    *ntiles_out = (int)cdiv(n, bn);
+}
+
+bool mlp_chain_layer_ok(int64_t k_total, int64_t n) {
+    if (n < 4 || n > 65536 || k_total < 32 || k_total > 65536) return false;
+    int bn, nt;
+    mlp_chain_tiling(n, &bn, &nt);
+    return bn <= mc::BN_MAX;
+}
+
+int mlp_chain_launch(mc::Program& prog, cudaStream_t st) {
+    if (prog.rows <= 0 || prog.nops <= 0) return 0;
+    O4D_REQUIRE(prog.nops <= mc::MAX_OPS, "mlp chain: too many layers in one launch (%d)", prog.nops);
+    prog.tiles = (int)cdiv(prog.rows, mc::BM);
+    double flops = 0.0;
+    for (int o = 0; o < prog.nops; ++o) {
+        mc::Op& op = prog.op[o];
+        O4D_REQUIRE(op.a1 && op.w && op.k1c >= 1 && op.bn >= 16 && op.bn <= mc::BN_MAX && op.bn % 16 == 0 && op.ntiles >= 1,
+                    "mlp chain: bad layer %d", o);
+        O4D_REQUIRE(!op.img || (op.n % 32 == 0 && op.img_cpt * 32 == op.n && (!op.bias || ((uintptr_t)op.bias & 15) == 0)),
+                    "mlp chain: an image output needs n %% 32 == 0 and a 16-byte aligned bias");
+        O4D_REQUIRE(op.img || op.out, "mlp chain: layer %d has no output", o);
+        O4D_REQUIRE(!op.img || ((!op.out || (op.ldo % 4 == 0 && ((uintptr_t)op.out & 15) == 0)) &&
+                                (!op.res || (op.ldr % 4 == 0 && ((uintptr_t)op.res & 15) == 0))),
+                    "mlp chain: layer %d writes an image next to an unaligned fp32 output", o);
+        op.n_img = op.img ? op.img_cpt * 32 : 0;
+        flops += 2.0 * (double)prog.rows * op.k_alg * op.n;
+    }
+    O4D_SMEM_ATTR(mc::mlp_chain_kernel, mc::SMEM_BYTES);
+    int grid = 148;
+    if (prog.tiles < grid) grid = prog.tiles;
+    ProfScope prof(PROF_LINEAR, flops, st);
+    mc::mlp_chain_kernel<<<grid, mc::THREADS, mc::SMEM_BYTES, st>>>(prog);
+    O4D_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---- ResnetBlockFC as ONE launch (C ABI, include/o4d.h) ------------------------------------------------------------
+struct ResblockWs {
+    uint8_t *img_x, *img_h, *w0p, *w1p;
+    size_t bytes;
+};
+static ResblockWs resblock_ws(int64_t rows, int d, int dh, void* base, size_t cap, bool* ok) {
+    Arena a(base, cap);
+    ResblockWs w;
+    w.img_x = a.get<uint8_t>(act_image_bytes(rows, d));
+    w.img_h = a.get<uint8_t>(act_image_bytes(rows, dh));
+    w.w0p = a.get<uint8_t>(tc_pack_bytes(dh, d));
+    w.w1p = a.get<uint8_t>(tc_pack_bytes(d, dh));
+    w.bytes = a.off;
+    if (ok) *ok = a.ok;
+    return w;
+}
+
+static bool resblock_ok(int64_t rows, int d, int dh) {
+    return rows >= 1 && d >= 32 && dh >= 32 && d % 32 == 0 && dh % 32 == 0 && mlp_chain_layer_ok(d, dh) && mlp_chain_layer_ok(dh, d);
+}
+
+}  // namespace o4d
+
+extern "C" size_t o4d_resblock_workspace_bytes(int64_t rows, int d, int d_hidden) {
+    if (!o4d::resblock_ok(rows, d, d_hidden)) return 0;
+    return o4d::resblock_ws(rows, d, d_hidden, nullptr, 0, nullptr).bytes;
+}
+
+extern "C" int o4d_resblock_forward_f32(const float* x, int64_t rows, int d, int64_t ldx, const float* w0, const float* b0,
+                                        int d_hidden, const float* w1, const float* b1, float* out, int64_t ldo,
+                                        int precision, void* workspace, size_t workspace_bytes, void* stream) {
+    using namespace o4d;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (rows == 0) return 0;
+    O4D_REQUIRE(x && w0 && w1 && out && workspace, "resblock: null pointer");
+    O4D_REQUIRE(precision == 1 || precision == 2, "resblock: the fused kernel is the tcgen05 path (precision 1 or 2)");
+    if (!resblock_ok(rows, d, d_hidden)) {
+        set_error("resblock: widths must be multiples of 32 within the chain kernel's tile limits (d=%d, d_hidden=%d)", d, d_hidden);
+        return O4D_E_UNSUPPORTED;
+    }
+    O4D_REQUIRE(ldx >= d && ldo >= d && ldx % 4 == 0 && ldo % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)out & 15) == 0 &&
+                    (!b0 || ((uintptr_t)b0 & 15) == 0) && (!b1 || ((uintptr_t)b1 & 15) == 0),
+                "resblock: rows and biases must be 16-byte aligned");
+    bool ok = false;
+    ResblockWs w = resblock_ws(rows, d, d_hidden, workspace, workspace_bytes, &ok);
+    if (!ok) {
+        set_error("resblock: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
+        return O4D_E_WORKSPACE;
+    }
+    O4D_TRY(tc_pack_launch(w0, d_hidden, d, d, w.w0p, st));
+    O4D_TRY(tc_pack_launch(w1, d, d_hidden, d_hidden, w.w1p, st));
+    O4D_TRY(act_image_launch(x, ldx, rows, d, 1, w.img_x, st));                 // implicit.py:93  act(x)
+    mc::Program prog;
+    prog.nops = 2;
+    prog.rows = rows;
+    prog.split = precision == 1 ? 1 : 0;
+    prog.tiles = 0;
+    mc::Op& f0 = prog.op[0];                                                    // net = fc_0(act(x)); image of act(net)
+    f0 = mc::Op{};
+    f0.a1 = w.img_x; f0.k1c = d / 32; f0.w = w.w0p; f0.bias = b0; f0.img = w.img_h; f0.img_cpt = d_hidden / 32; f0.img_relu = 1;
+    f0.n = d_hidden; f0.k_alg = d;
+    mlp_chain_tiling(d_hidden, &f0.bn, &f0.ntiles);
+    mc::Op& f1 = prog.op[1];                                                    // x + fc_1(act(net))   (implicit.py:94-101)
+    f1 = mc::Op{};
+    f1.a1 = w.img_h; f1.k1c = d_hidden / 32; f1.w = w.w1p; f1.bias = b1; f1.out = out; f1.ldo = ldo; f1.res = x; f1.ldr = ldx;
+    f1.n = d; f1.k_alg = d_hidden;
+    mlp_chain_tiling(d, &f1.bn, &f1.ntiles);
+    return mlp_chain_launch(prog, st);
+}

@@ -44,6 +44,9 @@ SIGNATURES = {
     'o4d_fps_f32': (c_int, [c_ptr, c_i64, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_size, c_ptr]),
     'o4d_linear_f32': (c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_i64,
                                c_int, c_int, c_ptr]),
+    'o4d_resblock_workspace_bytes': (c_size, [c_i64, c_int, c_int]),
+    'o4d_resblock_forward_f32': (c_int, [c_ptr, c_i64, c_int, c_i64, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_i64,
+                                         c_int, c_ptr, c_size, c_ptr]),
     'o4d_posenc_f32': (c_int, [c_ptr, c_i64, c_int, c_int, c_ptr, c_ptr]),
     'o4d_pt_block_workspace_bytes': (c_size, [c_i64, c_i64, c_int, c_int, c_int]),
     'o4d_pt_block_forward': (c_int, [c_ptr, c_ptr, c_i64, c_int, c_ptr, c_i64, c_ptr, c_i64, c_int, c_i64,

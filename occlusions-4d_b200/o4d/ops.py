@@ -141,6 +141,32 @@ def linear(x, weight, bias=None, residual=None, relu_in=False, relu_out=False, p
     return c.reshape(*lead, n)
 
 
+def resblock(x, w0, b0, w1, b1, precision=None):
+    """x + fc_1(relu(fc_0(relu(x)))) (ResnetBlockFC.forward, implicit.py:93-101) as one launch of the fused
+    multi-layer kernel; None when the shape or precision is outside it (the caller composes two dense layers)."""
+    prec = default_precision() if precision is None else int(precision)
+    x = _f32(x, 'x')
+    lead = x.shape[:-1]
+    a = x.reshape(-1, x.shape[-1]).contiguous()
+    d, dh = a.shape[1], w0.shape[0]
+    L = _lib.lib()
+    if prec == 0 or tuple(w0.shape) != (dh, d) or tuple(w1.shape) != (d, dh) or a.shape[0] < 1024:
+        return None
+    nbytes = L.o4d_resblock_workspace_bytes(a.shape[0], d, dh)
+    if nbytes == 0:
+        return None
+    w0c, w1c = _f32(w0.detach(), 'w0').contiguous(), _f32(w1.detach(), 'w1').contiguous()
+    b0c = _f32(b0.detach(), 'b0').contiguous() if b0 is not None else None
+    b1c = _f32(b1.detach(), 'b1').contiguous() if b1 is not None else None
+    with torch.cuda.device(a.device):
+        ws = workspace(a.device, nbytes, slot=4)
+        out = torch.empty_like(a)
+        rc = L.o4d_resblock_forward_f32(_ptr(a), a.shape[0], d, d, _ptr(w0c), _ptr(b0c), dh, _ptr(w1c), _ptr(b1c),
+                                        _ptr(out), d, prec, _ptr(ws), ws.numel(), _stream(a))
+    _lib.check(rc, 'o4d_resblock_forward_f32')
+    return out.reshape(*lead, d)
+
+
 # ---------------------------------------------------------------------------- attention
 
 def pt_layer_forward(params, x, pos, x2, pos2, k, precision=None, return_idx=False):

@@ -146,6 +146,33 @@ def test_linear_matches_fp64(rows, k, n):
         assert relerr(got2.cpu().double(), plain) < tol, (prec, rows, k, n)
 
 
+@pytest.mark.parametrize('rows,d,dh', [(1024, 416, 416), (3001, 416, 416), (40000, 416, 416), (2500, 96, 160),
+                                       (1500, 288, 832)])
+def test_fused_residual_block_matches_fp64(rows, d, dh):
+    """ResnetBlockFC.forward (implicit.py:93-101) as ONE launch of the fused multi-layer kernel: ragged last tile,
+    several row tiles per CTA (40000 rows = 313 tiles on 148 CTAs), 1 / 2 / 4 n-tiles, image hand-off fc_0 -> fc_1."""
+    g = torch.Generator().manual_seed(rows + d)
+    x = torch.randn(rows, d, generator=g) * 3.0
+    w0 = torch.randn(dh, d, generator=g) / math.sqrt(d)
+    b0 = torch.randn(dh, generator=g)
+    w1 = torch.randn(d, dh, generator=g) / math.sqrt(dh)
+    b1 = torch.randn(d, generator=g)
+    h = torch.relu(x.double()) @ w0.double().t() + b0.double()
+    want = x.double() + torch.relu(h) @ w1.double().t() + b1.double()
+    got = ops.resblock(x.to(DEV), w0.to(DEV), b0.to(DEV), w1.to(DEV), b1.to(DEV), precision=1)
+    assert got is not None, 'shape should be inside the fused kernel'
+    assert relerr(got.cpu().double(), want) < TOL_SPLIT, relerr(got.cpu().double(), want)
+    # same launch twice: persistent-kernel state (barrier phases, counters) starts clean every time
+    again = ops.resblock(x.to(DEV), w0.to(DEV), b0.to(DEV), w1.to(DEV), b1.to(DEV), precision=1)
+    assert torch.equal(again, got)
+    # the per-layer kernels must agree with it to rounding (same bf16x3 arithmetic, different tiling of the sum)
+    two = ops.linear(ops.linear(x.to(DEV), w0.to(DEV), b0.to(DEV), relu_in=True, precision=1), w1.to(DEV), b1.to(DEV),
+                     residual=x.to(DEV), relu_in=True, precision=1)
+    assert relerr(got.cpu().double(), two.cpu().double()) < TOL_SPLIT
+    assert ops.resblock(x.to(DEV)[:, :40].contiguous(), w0.to(DEV)[:, :40].contiguous(), b0.to(DEV), w1.to(DEV)[:40].contiguous(),
+                        b1.to(DEV)[:40].contiguous(), precision=1) is None      # width 40: not a whole image chunk
+
+
 def test_linear_strided_views_and_inplace_residual():
     g = torch.Generator().manual_seed(9)
     base = torch.randn(500, 291, generator=g)

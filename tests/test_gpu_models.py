@@ -206,7 +206,12 @@ def test_full_size_encoder_is_deterministic(c2):
 
 # ------------------------------------------------------------ released checkpoints
 
-TOL_FP64 = 1e-4     # distance to the fp64 arbitration run (the reference's own fp32 forward sits at ~2e-4)
+# Distance to the fp64 arbitration run.  Measured on the B200 (tools/ckpt_error.py, profiles/r2_a_ckpt_error.json): with the
+# released weights (logits to 362) every fp32-accumulating implementation sits at 2-5e-4 from fp64 -- the unmodified
+# reference's own forward 2.3e-4 (GREATER) / 1.6e-4 (CARLA), our fp32 CUDA-core path 3.9e-4 / 3.4e-4, bf16x3 3.9e-4 /
+# 9.7e-4 -- so the north-star bar (1e-3) is the bound, and the path must also stay within 8x of the reference's own
+# fp32 rounding distance.
+TOL_FP64 = 1e-3
 
 
 @pytest.mark.parametrize('which', ['greater', 'carla'])
@@ -242,6 +247,7 @@ def test_released_checkpoint_parity(which):
     print('%s checkpoint: largest |logit| %.1f; ours vs reference %.2e, ours vs fp64 %.2e, reference vs fp64 %.2e'
           % (which, float(out.abs().max()), e_ref, e64, ref64))
     assert e64 < TOL_FP64 and e64_pen < TOL_FP64, (e64, e64_pen)
+    assert e64 < 8 * max(ref64, 1e-4), (e64, ref64)
     # the large-logit regime is on record (SURVEY hard part 1: GREATER logits reach several hundred)
     assert abs(float(out.abs().max()) - float(ck['max_abs_logit'])) < 1e-2 * float(ck['max_abs_logit'])
     if which == 'greater':

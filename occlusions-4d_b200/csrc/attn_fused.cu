@@ -28,6 +28,7 @@
 // How the kernel got here (what bound it at each step, measured): DESIGN.md section 4.
 #include "o4d_common.cuh"
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 namespace o4d {
 namespace fa {
@@ -333,7 +334,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fused_kernel(const Params p) 
         }
         const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         // ---- gather staging (see G_PITCH): this warp copies 16 Ka rows and up to 2 Qa rows per chunk
-        __syncwarp(); asm volatile("bar.sync 1, 256;" ::: "memory");                 // s_j complete
+        asm volatile("barrier.sync 1, 256;" ::: "memory");                 // s_j complete
         const int g_piece = lane & 7, g_sub = lane >> 3;
         const int g_rbase = (warp & 3) * 32 + (warp >> 2) * 16;
         int gj[4];
@@ -440,7 +441,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fused_kernel(const Params p) 
                            p.vtab + (int64_t)gj[it] * d + cc * 32 + g_piece * 4);
         };
         // every warp has consumed the last Ka/Qa stage (its G_EMPTY arrival precedes this barrier)
-        __syncwarp(); asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("barrier.sync 1, 256;" ::: "memory");
         issue_v(0, 0);
         if (ND > 1) issue_v(1, 1);
         cp_async_commit();
@@ -449,7 +450,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fused_kernel(const Params p) 
             const int gn = min(GROUP, ND - g0);
             if (dbg) t0 = clock64();
             cp_async_wait_all();
-            __syncwarp(); asm volatile("bar.sync 2, 288;" ::: "memory");         // V slices landed; previous group's tiles are free
+            asm volatile("barrier.sync 2, 288;" ::: "memory");         // V slices landed; previous group's tiles are free
             if (dbg) t_bar += clock64() - t0;
 #pragma unroll
             for (int u = 0; u < GROUP; ++u) {
@@ -491,7 +492,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fused_kernel(const Params p) 
                 if (dbg) t_stage += clock64() - t0;
             }
             if (dbg) t0 = clock64();
-            __syncwarp(); asm volatile("bar.sync 2, 288;" ::: "memory");         // the group's tiles are complete, V stages consumed
+            asm volatile("barrier.sync 2, 288;" ::: "memory");         // the group's tiles are complete, V stages consumed
             if (dbg) { const long long t1 = clock64(); t_bar += t1 - t0; t0 = t1; }
             if (g0 + GROUP < ND) {                                  // next group's V slices: in flight during the reduce
                 issue_v(g0 + GROUP, 0);
@@ -530,8 +531,10 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fused_kernel(const Params p) 
                 const int s = c & 1;
                 const uint32_t use = (uint32_t)(c >> 1);
                 mbar_wait(BAR(W_EMPTY + s), (use & 1u) ^ 1u);
-                mbar_arrive_expect_tx(BAR(W_FULL + s), (uint32_t)w2);
-                bulk_g2s(smem_base + OFF_W + s * w2, p.wmain + (size_t)c * wpacked + 2 * WC_BYTES, (uint32_t)w2, BAR(W_FULL + s));
+                // [W_a2 hi][W_a2 lo]; split 2 never reads the lo image: half the bytes of the dominant stream
+                const uint32_t wbytes = p.split == 2 ? (uint32_t)(w2 / 2) : (uint32_t)w2;
+                mbar_arrive_expect_tx(BAR(W_FULL + s), wbytes);
+                bulk_g2s(smem_base + OFF_W + s * w2, p.wmain + (size_t)c * wpacked + 2 * WC_BYTES, wbytes, BAR(W_FULL + s));
             }
             // W_p2 image into W stage 0 for the delta contraction (NC is even: this is use NC/2 of stage 0)
             const uint32_t use = (uint32_t)(NC >> 1);
@@ -544,8 +547,8 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fused_kernel(const Params p) 
         const int64_t q0 = (int64_t)blockIdx.x * p.tq;
         for (int g0 = 0; g0 < ND; g0 += EPI_GROUP) {
             const int gn = min(EPI_GROUP, ND - g0);
-            __syncwarp(); asm volatile("bar.sync 2, 288;" ::: "memory");
-            __syncwarp(); asm volatile("bar.sync 2, 288;" ::: "memory");         // the group's tiles are complete
+            asm volatile("barrier.sync 2, 288;" ::: "memory");
+            asm volatile("barrier.sync 2, 288;" ::: "memory");         // the group's tiles are complete
             const int ntask = gn * p.tq;
             for (int task = ROW_WARPS; task < ntask; task += EPI_WARPS) {
                 const int u = task >= p.tq ? 1 : 0, q = task - u * p.tq;
@@ -730,9 +733,22 @@ __global__ void fused_pack_kernel(const float* __restrict__ wc, const float* __r
 
 }  // namespace fa
 
-// Experiment knob (diagnostics, o4d_debug_set_fused_passes): which of the three bf16x3 products the logits
-// contraction issues.  1 = all three (default), 2 = drop hidden_hi * W_lo, 3 = drop hidden_lo * W_hi.
-static std::atomic<int> g_fused_mma2_mode{1};
+// Which of the three bf16x3 products the LOGITS contraction (hidden -> logits, 81 % of the decoder's flops) issues:
+// 1 = all three, 2 = hidden_hi W_hi + hidden_lo W_hi (W_a2 rounded to bf16, the hidden layer keeps its 16-bit split),
+// 3 = drop hidden_lo W_hi instead (diagnostics only: 5e-2 .. 2e-1 on the released checkpoints).
+// Default 2.  Measured on the released checkpoints against the fp64 arbitration run (profiles/r2_a_ckpt_error.json,
+// r2_c_ckpt_error.json): GREATER 6.1e-4 (mode 1) vs 6.3e-4 (mode 2), CARLA 9.7e-4 vs 8.8e-4 -- indistinguishable,
+// while the reference's own fp32 forward sits at 2.3e-4 / 1.6e-4.  Why the weight rounding is harmless here and the
+// hidden rounding is not: the rounding error of W_a2 is the SAME perturbation for all k neighbours of a query, and the
+// per-channel softmax over neighbours only sees differences between their logits; rounding the hidden activations
+// perturbs every (query, neighbour) pair independently.  What it buys: one third of the kernel's MMA work and half of
+// its weight stream (the main loop is bound by the L2 -> SM stream of W_a2: 57 KB per 32-unit chunk per SM, in-kernel
+// stamps in DESIGN.md section 4).  O4D_FUSED_LOGIT_PASSES=3 (or o4d_debug_set_fused_passes(1)) restores all three.
+static int fused_mode_default() {
+    const char* e = getenv("O4D_FUSED_LOGIT_PASSES");
+    return (e && e[0] == '3') ? 1 : 2;
+}
+static std::atomic<int> g_fused_mma2_mode{0};   // 0 = not set: environment / default
 
 bool attn_fused_supported(int d, int k) {
     if (d % 32 != 0 || d < 288 || d > 416 || k < 8 || k > O4D_MAX_K) return false;  // k >= 8: at most 16 queries per tile
@@ -771,7 +787,11 @@ int attn_fused_launch(const PtBlockParams& P, const AttnTables& T, const float* 
     p.wmain = (const uint8_t*)T.fused;
     p.wp2 = (const uint8_t*)T.fused + align_up((size_t)NC * fa::wstage_bytes(d), 256);
     p.out = out;
-    p.n = n; p.d = d; p.k = k; p.tq = fa::BM / k; p.split = (precision == 1) ? g_fused_mma2_mode.load(std::memory_order_relaxed) : 0;
+    p.n = n; p.d = d; p.k = k; p.tq = fa::BM / k; {
+        int mode = g_fused_mma2_mode.load(std::memory_order_relaxed);
+        if (mode == 0) mode = fused_mode_default();
+        p.split = (precision == 1) ? mode : 0;
+    }
     p.scale_log2 = (float)(1.4426950408889634 / sqrt((double)d));
     const int64_t tiles = cdiv(n, p.tq);
     // algorithmic flops of what this launch replaces (reference formulation): per pair 2*(3*32 + 32*d) +
@@ -791,7 +811,7 @@ int attn_fused_launch(const PtBlockParams& P, const AttnTables& T, const float* 
 
 }  // namespace o4d
 
-extern "C" void o4d_debug_set_fused_passes(int mode) { o4d::g_fused_mma2_mode.store(mode >= 1 && mode <= 3 ? mode : 1); }
+extern "C" void o4d_debug_set_fused_passes(int mode) { o4d::g_fused_mma2_mode.store(mode >= 1 && mode <= 3 ? mode : 0); }
 extern "C" int o4d_debug_read(long long* out16) {
     return (int)cudaMemcpyFromSymbol(out16, o4d::fa::g_dbg, sizeof(long long) * 16);
 }

@@ -88,6 +88,7 @@ static int pe_width(const o4d_decoder_config* c) {
 }
 
 static size_t packed_total_bytes(const o4d_decoder_config* c);
+static bool dec_chain_possible(const o4d_decoder_config* c);
 
 static SceneView scene_view(const o4d_decoder_config* c, int64_t m, void* base) {
     Arena a(base ? base : nullptr, base ? (size_t)-1 : 0);
@@ -172,6 +173,7 @@ static void packed_set(const o4d_decoder_config* c, const DecParams& d, const Sc
         ps->add(w, p);
         p += align_up(tc_pack_bytes(n, k), 256);
     });
+    ps->pair = dec_chain_possible(c) && mlp_chain_pair();
 }
 
 int decoder_prepare(const o4d_decoder_config* c, const float* const* P, const float* pcl_abstract, int64_t m,
@@ -232,7 +234,8 @@ int decoder_prepare(const o4d_decoder_config* c, const float* const* P, const fl
         char* p = (char*)scene + s.pack_off;
         int rc = 0;
         for_each_tc_weight(c, d, &s, m, [&](const float* w, int n, int k, int ldw) {
-            if (rc == 0) rc = tc_pack_launch(w, n, k, ldw, p, st);
+            // the fused multi-layer kernel is the only reader of these images whenever it can run (format: mlp_chain.cu)
+            if (rc == 0) rc = dec_chain_possible(c) ? mlp_chain_pack_launch(w, n, k, ldw, p, st) : tc_pack_launch(w, n, k, ldw, p, st);
             p += align_up(tc_pack_bytes(n, k), 256);
         });
         O4D_TRY(rc);
@@ -262,7 +265,7 @@ static bool dec_chain_possible(const o4d_decoder_config* c) {
     if (!env || c->precision == 0) return false;
     const int H = c->d_hidden, E = c->d_latent_local;
     const int in_w = c->pos_encoding_freqs > 0 ? c->d_in * (2 * c->pos_encoding_freqs + 1) : c->d_in;
-    if (H % 32 != 0 || H < 32) return false;
+    if (H % 32 != 0 || H < 32 || in_w < 32 || c->d_out < 4) return false;   // (tc_shape_ok of every layer of the path)
     if (c->cross_attn_layers > 0 && !attn_fused_supported(H, c->cross_attn_neighbors)) return false;
     return mlp_chain_layer_ok(H, H) && mlp_chain_layer_ok(H, 2 * H) && mlp_chain_layer_ok(H, c->d_out) &&
            mlp_chain_layer_ok((in_w + 31) / 32 * 32 + E, H) && mlp_chain_layer_ok(H + E, H);
@@ -446,8 +449,13 @@ int decoder_forward(const o4d_decoder_config* c, const float* const* P, const vo
     const float* in_ptr = c->pos_encoding_freqs > 0 ? w.pe : query;
     const int in_w = c->pos_encoding_freqs > 0 ? pe_w : c->d_in;
     if (c->pos_encoding_freqs > 0) O4D_TRY(posenc_launch(query, nq, c->d_in, c->pos_encoding_freqs, w.pe, st));
-    if (fold && w.img_x && tc_shape_ok(nq, H, c->d_out))
+    if (w.img_x && nq >= 1024) {
+        if (!fold) {
+            set_error("decoder: fused MLP path selected but the folded weights are missing");
+            return O4D_E_ARG;
+        }
         return decoder_forward_chain(c, d, s, ps, w, m, query, in_ptr, in_w, nq, out, penult, st);
+    }
     if (fold)
         O4D_TRY(linear_ps_launch(&ps, in_ptr, nq, in_w, in_w, s.wcat[0], s.kcat[0], s.bcat[0], H, nullptr, 0, w.x, H, 0,
                                  prec, st, &cat));

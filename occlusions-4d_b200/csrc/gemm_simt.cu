@@ -143,7 +143,7 @@ int linear_ps_launch(const PackedSet* ps, const float* A, int64_t rows, int64_t 
                      int64_t ldc, int flags, int precision, cudaStream_t st, const RowGather* g) {
     ProfScope prof(PROF_LINEAR, 2.0 * (double)rows * (double)(k + (g ? g->k2 : 0)) * (double)n, st);
     if (precision != 0 && tc_shape_ok(rows, k, n)) {
-        const void* packed = ps ? ps->find(W) : nullptr;
+        const void* packed = (ps && !ps->pair) ? ps->find(W) : nullptr;
         if (packed)
             return linear_tc_packed_launch(A, rows, k, lda, packed, n, bias, R, ldr, C, ldc, flags, precision, st, g);
     }

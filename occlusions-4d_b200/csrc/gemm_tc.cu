@@ -93,6 +93,7 @@ __device__ __forceinline__ uint32_t umma_idesc(int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
+
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -166,6 +167,32 @@ __global__ void pack_weight_kernel(const float* __restrict__ W, int64_t ldw, Pac
         split_bf16(v, hi, lo);
         out[slab * 2 * slab_elems + within] = hi;
         out[slab * 2 * slab_elems + slab_elems + within] = lo;
+    }
+}
+
+// Pair format (mlp_chain.cu, cta_group::2): per (n-tile, k-chunk) [half 0: hi, lo][half 1: hi, lo], half h = rows
+// [h * bn/2, (h+1) * bn/2) of the tile, each image [kc = 4][row-group][8 rows][8 bf16]: exactly what CTA h of a pair
+// copies into its shared memory.  Same total size as the single-CTA format.
+__global__ void pack_weight_pair_kernel(const float* __restrict__ W, int64_t ldw, PackMeta m, __nv_bfloat16* __restrict__ out) {
+    const int64_t slab_elems = (int64_t)m.bn * BK;
+    const int64_t total = (int64_t)m.ntiles * m.kchunks * slab_elems;
+    const int hb = m.bn / 2;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t slab = e / slab_elems;
+        const int within = (int)(e % slab_elems);
+        const int t = (int)(slab / m.kchunks), c = (int)(slab % m.kchunks);
+        const int half = within / (hb * BK);
+        const int w2 = within % (hb * BK);
+        const int kc = w2 / (hb * 8);
+        const int rem = w2 % (hb * 8);
+        const int row = rem / 8, el = rem % 8;
+        const int gn = t * m.bn + half * hb + row, gk = c * BK + kc * 8 + el;
+        float v = (gn < m.n && gk < m.k) ? W[(int64_t)gn * ldw + gk] : 0.f;
+        __nv_bfloat16 hi, lo;
+        split_bf16(v, hi, lo);
+        __nv_bfloat16* dst = out + slab * 2 * slab_elems + (int64_t)half * 2 * hb * BK;
+        dst[w2] = hi;
+        dst[hb * BK + w2] = lo;
     }
 }
 
@@ -434,21 +461,6 @@ linear_tc_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda, 
 
 }  // namespace tc
 
-// Persistent warp-specialized variant, gemm_tcp.cu (same packed-weight format).  Opt-in (O4D_TC_PERSIST=1):
-// parity green, but measured slower than this kernel (dense family 27.8 vs 22.0 ms per step, see gemm_tcp.cu).
-int linear_tcp_packed_launch(const float* A, int64_t rows, int64_t k, int64_t lda, const void* packed, int64_t n,
-                             const float* bias, const float* R, int64_t ldr, float* C, int64_t ldc, int flags,
-                             int precision, cudaStream_t st, const RowGather* gp);
-static bool tc_persistent(int64_t rows, int64_t n, int64_t ktot) {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("O4D_TC_PERSIST");
-        v = (e && e[0] == '1') ? 1 : 0;
-    }
-    // worth it once every SM has at least two tiles to overlap
-    return v == 1 && cdiv(rows, tc::BM) * tc::pack_meta((int)n, (int)ktot).ntiles >= 2 * 148;
-}
-
 size_t tc_pack_bytes(int64_t n, int64_t k) { return tc::pack_bytes(tc::pack_meta((int)n, (int)k)); }
 
 int tc_pack_launch(const float* W, int64_t n, int64_t k, int64_t ldw, void* packed, cudaStream_t st) {
@@ -461,6 +473,16 @@ int tc_pack_launch(const float* W, int64_t n, int64_t k, int64_t ldw, void* pack
     return 0;
 }
 
+int tc_pack_pair_launch(const float* W, int64_t n, int64_t k, int64_t ldw, void* packed, cudaStream_t st) {
+    tc::PackMeta m = tc::pack_meta((int)n, (int)k);
+    const int64_t total = (int64_t)m.ntiles * m.kchunks * m.bn * tc::BK;
+    int64_t blocks = cdiv(total, 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    tc::pack_weight_pair_kernel<<<(unsigned)blocks, 256, 0, st>>>(W, ldw, m, (__nv_bfloat16*)packed);
+    O4D_LAUNCH_CHECK();
+    return 0;
+}
+
 // n >= 8: narrow outputs (lin_out, 9 .. 33 columns) run as one 16/32/48-column UMMA tile; the CUDA-core kernel
 // took as long for 416 -> 9 as the tensor-core kernel for 416 -> 416 (69 us per 32768 rows).
 bool tc_shape_ok(int64_t rows, int64_t k, int64_t n) { return rows >= 1024 && k >= 32 && n >= 4 && k <= 65536 && n <= 65536; }
@@ -469,9 +491,6 @@ int linear_tc_packed_launch(const float* A, int64_t rows, int64_t k, int64_t lda
                             const float* bias, const float* R, int64_t ldr, float* C, int64_t ldc, int flags,
                             int precision, cudaStream_t st, const RowGather* gp) {
     if (rows == 0) return 0;
-    const int64_t ktot_ = gp && gp->a2 ? cdiv(k, tc::BK) * tc::BK + gp->k2 : k;
-    if (tc_persistent(rows, n, ktot_))
-        return linear_tcp_packed_launch(A, rows, k, lda, packed, n, bias, R, ldr, C, ldc, flags, precision, st, gp);
     RowGather g;
     if (gp) g = *gp;
     O4D_SMEM_ATTR(tc::linear_tc_kernel, tc::SMEM_BYTES);

@@ -24,6 +24,7 @@
 #include "o4d_common.cuh"
 #include "tc_helpers.cuh"
 #include "mlp_chain.cuh"
+#include <stdlib.h>
 
 namespace o4d {
 namespace mc {
@@ -65,6 +66,16 @@ __device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
     return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
 
+// PAIR = true: two CTAs of a cluster (one TPC) work as a pair (tcgen05 cta_group::2).  Each owns one 128-row tile of a
+// tile pair and its own A-image stream, but loads only HALF of every weight slab; the leader's MMA thread issues
+// M = 256 instructions that read B half from each CTA's shared memory.  Weight bytes per SM halve: 42.6 -> 29.3 KB
+// per (128 x 208 x 32) chunk = 624 tensor cycles, i.e. 68 -> 47 B/clk per SM against the ~43 B/clk per SM the L2 can
+// deliver chip-wide (the single-CTA kernel sits at 0.59 of the tensor peak for exactly this reason).
+//   full[s]      leader: own expect_tx + the peer's forwarder (peer warp 9 waits for the peer's own full[s], then arrives
+//                remotely); peer: own expect_tx
+//   empty[s], acc_full[a]   tcgen05.commit ... multicast -> the barrier at the same offset in both CTAs
+//   acc_empty[a] leader only: 8 local + 8 remote epilogue-warp arrivals
+template <bool PAIR>
 __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const Program P) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -76,30 +87,46 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const Program P) 
     const uint32_t accf0 = smem_u32(&bars[2 * STAGES]), acce0 = smem_u32(&bars[2 * STAGES + 2]);
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t done0 = smem_u32(done);
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;   // 0 = leader (issues the pair's MMAs), 1 = peer
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(full0 + 8 * s, 1);                // the producer's arrive.expect_tx (+ the copies' bytes)
+            mbar_init(full0 + 8 * s, (PAIR && rank == 0) ? 2 : 1);   // the producer's arrive.expect_tx (+ bytes) [+ the peer's forwarder]
             mbar_init(empty0 + 8 * s, 1);               // one tcgen05.commit
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(accf0 + 8 * a, 1);                // one tcgen05.commit
-            mbar_init(acce0 + 8 * a, EPI_WARPS);        // every epilogue warp has drained the accumulator
+            mbar_init(acce0 + 8 * a, PAIR ? 2 * EPI_WARPS : EPI_WARPS);   // every epilogue warp (of both CTAs) has drained it
         }
         for (int w = 0; w < EPI_WARPS; ++w) done[w] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == EPI_WARPS + 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();      // both CTAs' mbarriers are initialised and TMEM allocated before any remote arrive / MMA
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    // row tiles of this CTA: blockIdx.x, + gridDim.x, ...
-    const int ntl = (P.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    // work units of this CTA (pair): unit, unit + nunits, ...; a unit is a row tile, or a PAIR of row tiles (2u, 2u + 1)
+    // of which this CTA takes tile 2u + rank
+    const int unit0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int nunits = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int tunits = PAIR ? (P.tiles + 1) >> 1 : P.tiles;
+    const int ntl = (tunits - unit0 + nunits - 1) / nunits;
+    auto tile_of = [&](int j) -> int64_t {
+        const int64_t u = (int64_t)unit0 + (int64_t)j * nunits;
+        return PAIR ? 2 * u + rank : u;
+    };
 
     if (warp < EPI_WARPS) {
         // ================================================================== epilogue warps
@@ -119,12 +146,13 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const Program P) 
                                 (!op.res || ((op.ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(op.res) & 15) == 0))) &&
                                 (!op.bias || ((reinterpret_cast<uintptr_t>(op.bias) & 15) == 0));
             for (int j = 0; j < ntl; ++j) {
-                const int64_t tile = (int64_t)blockIdx.x + (int64_t)j * gridDim.x;
+                const int64_t tile = tile_of(j);
                 const int64_t row0 = tile * BM + quarter * 32;          // first row of this warp
                 const int rows_here = (int)max((int64_t)0, min((int64_t)32, P.rows - row0));
                 for (int nh = 0; nh < op.ntiles; ++nh, ++item) {
                     const int acc = item & 1;
-                    mbar_wait(accf0 + 8 * acc, (uint32_t)(item >> 1) & 1u);
+                    if (PAIR) mbar_wait_cl(accf0 + 8 * acc, (uint32_t)(item >> 1) & 1u);
+                    else mbar_wait(accf0 + 8 * acc, (uint32_t)(item >> 1) & 1u);
                     tc_fence_after();
                     const uint32_t taddr = taddr_q + (uint32_t)(acc * 256);
                     const int col_base = nh * bn;
@@ -237,7 +265,10 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const Program P) 
                     // accumulator drained -> the MMA issuer may overwrite it (item + 2)
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(acce0 + 8 * acc);
+                    if (lane == 0) {
+                        if (PAIR && rank != 0) mbar_arrive_cluster(acce0 + 8 * acc, 0);   // the leader's MMA thread waits for both CTAs
+                        else mbar_arrive(acce0 + 8 * acc);
+                    }
                     // this warp's part of the item is in global memory: make it visible to the TMA engine (async
                     // proxy) of this CTA before the producer is told (generic stores -> fence -> flag)
                     __threadfence();
@@ -255,10 +286,11 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const Program P) 
             int prev_nt = 0;      // n-tiles per row tile of the previous op
             for (int o = 0; o < P.nops; ++o) {
                 const Op& op = P.op[o];
-                const uint32_t w_bytes = (uint32_t)(2 * op.bn * BK * 2);
+                // bytes of this CTA's share of a weight slab: the whole [hi][lo] slab, or (pair format) half `rank` of it
+                const uint32_t w_bytes = (uint32_t)(2 * op.bn * BK * 2) / (PAIR ? 2u : 1u);
                 const int nch = op.k1c + op.k2c;
                 for (int j = 0; j < ntl; ++j) {
-                    const int64_t tile = (int64_t)blockIdx.x + (int64_t)j * gridDim.x;
+                    const int64_t tile = tile_of(j);
                     if (o > 0) {
                         // the images this op reads were written by the previous op's epilogues of THIS tile: wait
                         // until every epilogue warp has finished its last item of (o - 1, j)
@@ -276,16 +308,19 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const Program P) 
                     const uint8_t* a1 = op.a1 + (size_t)tile * op.k1c * IMG_CHUNK_BYTES;
                     const uint8_t* a2 = op.a2 ? op.a2 + (size_t)tile * op.k2c * IMG_CHUNK_BYTES : nullptr;
                     for (int nh = 0; nh < op.ntiles; ++nh) {
-                        const uint8_t* wsrc = op.w + (size_t)nh * nch * w_bytes;
+                        // packed per (n-tile, k-chunk): [hi slab][lo slab], or in pair format [half 0: hi, lo][half 1: hi, lo]
+                        const size_t w_stride = PAIR ? 2 * (size_t)w_bytes : (size_t)w_bytes;
+                        const uint8_t* wsrc = op.w + (size_t)nh * nch * w_stride + (PAIR ? (size_t)rank * w_bytes : 0);
                         for (int c = 0; c < nch; ++c, ++g) {
                             const int s = g % STAGES;
                             const uint32_t ph = (uint32_t)(g / STAGES) & 1u;
-                            mbar_wait(empty0 + 8 * s, ph ^ 1u);
+                            if (PAIR) mbar_wait_cl(empty0 + 8 * s, ph ^ 1u);
+                            else mbar_wait(empty0 + 8 * s, ph ^ 1u);
                             const uint32_t dst = smem_base + s * STAGE_BYTES;
                             mbar_arrive_expect_tx(full0 + 8 * s, IMG_CHUNK_BYTES + w_bytes);
                             const uint8_t* asrc = c < op.k1c ? a1 + (size_t)c * IMG_CHUNK_BYTES : a2 + (size_t)(c - op.k1c) * IMG_CHUNK_BYTES;
                             bulk_g2s(dst, asrc, IMG_CHUNK_BYTES, full0 + 8 * s);
-                            bulk_g2s(dst + IMG_CHUNK_BYTES, wsrc + (size_t)c * w_bytes, w_bytes, full0 + 8 * s);
+                            bulk_g2s(dst + IMG_CHUNK_BYTES, wsrc + (size_t)c * w_stride, w_bytes, full0 + 8 * s);
                         }
                     }
                 }
@@ -294,28 +329,31 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const Program P) 
             }
         }
     } else {
-        // ================================================================== MMA issuer
-        if (lane == 0) {
+        // ================================================================== MMA issuer (pair: the leader's; the peer's warp forwards)
+        if (lane == 0 && rank == 0) {
             int g = 0, item = 0;
             const uint32_t lbo_a = BM * 16;
             for (int o = 0; o < P.nops; ++o) {
                 const Op& op = P.op[o];
                 const int bn = op.bn;
-                const uint32_t idesc = umma_idesc(bn);
-                const uint32_t lbo_b = (uint32_t)bn * 16;
-                const uint32_t b_half = (uint32_t)bn * BK * 2;
+                const int hb = PAIR ? bn / 2 : bn;                       // B rows in THIS CTA's shared memory
+                const uint32_t idesc = PAIR ? umma_idesc_pair(bn) : umma_idesc(bn);
+                const uint32_t lbo_b = (uint32_t)hb * 16;
+                const uint32_t b_half = (uint32_t)hb * BK * 2;
                 const int nch = op.k1c + op.k2c;
                 for (int j = 0; j < ntl; ++j) {
                     for (int nh = 0; nh < op.ntiles; ++nh, ++item) {
                         const int acc = item & 1;
                         // accumulator free?  (its previous user was item - 2)
-                        mbar_wait(acce0 + 8 * acc, ((uint32_t)(item >> 1) & 1u) ^ 1u);
+                        if (PAIR) mbar_wait_cl(acce0 + 8 * acc, ((uint32_t)(item >> 1) & 1u) ^ 1u);
+                        else mbar_wait(acce0 + 8 * acc, ((uint32_t)(item >> 1) & 1u) ^ 1u);
                         tc_fence_after();
                         const uint32_t dcol = tmem_base + (uint32_t)(acc * 256);
                         for (int c = 0; c < nch; ++c, ++g) {
                             const int s = g % STAGES;
                             const uint32_t ph = (uint32_t)(g / STAGES) & 1u;
-                            mbar_wait(full0 + 8 * s, ph);
+                            if (PAIR) mbar_wait_cl(full0 + 8 * s, ph);
+                            else mbar_wait(full0 + 8 * s, ph);
                             tc_fence_after();
                             const uint32_t a_hi = smem_base + s * STAGE_BYTES;
                             const uint32_t a_lo = a_hi + A_HALF;
@@ -325,26 +363,51 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const Program P) 
                             for (int ks = 0; ks < BK / 16; ++ks) {
                                 const uint64_t da_hi = umma_desc(a_hi + ks * 2 * lbo_a, lbo_a, 128);
                                 const uint64_t db_hi = umma_desc(b_hi + ks * 2 * lbo_b, lbo_b, 128);
-                                umma_f16(dcol, da_hi, db_hi, idesc, (c | ks) ? 1u : 0u);
-                                if (P.split) {
-                                    const uint64_t da_lo = umma_desc(a_lo + ks * 2 * lbo_a, lbo_a, 128);
-                                    const uint64_t db_lo = umma_desc(b_lo + ks * 2 * lbo_b, lbo_b, 128);
-                                    umma_f16(dcol, da_lo, db_hi, idesc, 1u);
-                                    umma_f16(dcol, da_hi, db_lo, idesc, 1u);
+                                const uint64_t da_lo = umma_desc(a_lo + ks * 2 * lbo_a, lbo_a, 128);
+                                const uint64_t db_lo = umma_desc(b_lo + ks * 2 * lbo_b, lbo_b, 128);
+                                if (PAIR) {
+                                    umma_f16_pair(dcol, da_hi, db_hi, idesc, (c | ks) ? 1u : 0u);
+                                    if (P.split) {
+                                        umma_f16_pair(dcol, da_lo, db_hi, idesc, 1u);
+                                        umma_f16_pair(dcol, da_hi, db_lo, idesc, 1u);
+                                    }
+                                } else {
+                                    umma_f16(dcol, da_hi, db_hi, idesc, (c | ks) ? 1u : 0u);
+                                    if (P.split) {
+                                        umma_f16(dcol, da_lo, db_hi, idesc, 1u);
+                                        umma_f16(dcol, da_hi, db_lo, idesc, 1u);
+                                    }
                                 }
                             }
-                            umma_commit(empty0 + 8 * s);          // frees the stage when these MMAs retire
+                            if (PAIR) umma_commit_pair(empty0 + 8 * s);   // frees the stage (in both CTAs) when these MMAs retire
+                            else umma_commit(empty0 + 8 * s);
                         }
-                        umma_commit(accf0 + 8 * acc);             // accumulator complete -> epilogue
+                        if (PAIR) umma_commit_pair(accf0 + 8 * acc);      // accumulator complete -> epilogues (of both CTAs)
+                        else umma_commit(accf0 + 8 * acc);
                     }
+                }
+            }
+        } else if (PAIR && lane == 0) {
+            // peer: tell the leader's MMA thread when THIS CTA's share of a stage (its A rows, its half of the weight
+            // slab) has landed.  A stage cannot be refilled before the leader has consumed it, so no phase is skipped.
+            int g = 0;
+            for (int o = 0; o < P.nops; ++o) {
+                const int total = ntl * P.op[o].ntiles * (P.op[o].k1c + P.op[o].k2c);
+                for (int i = 0; i < total; ++i, ++g) {
+                    const int s = g % STAGES;
+                    mbar_wait(full0 + 8 * s, (uint32_t)(g / STAGES) & 1u);
+                    mbar_arrive_cluster(full0 + 8 * s, 0);
                 }
             }
         }
     }
+    tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();      // the peer's TMEM / shared memory stay valid until the leader's last MMA has retired
     if (warp == EPI_WARPS + 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
@@ -396,8 +459,28 @@ __global__ void image_from_f32_kernel(const float* __restrict__ src, int64_t ld,
 
 }  // namespace mc
 
+// O4D_CHAIN_PAIR=1 selects the CTA-pair (cta_group::2) instantiation.  Measured on the B200 (profiles/r2_c_bench_*):
+// parity green, but SLOWER than the single-CTA kernel -- dense family 18.9 vs 15.2 ms per step -- although it moves a
+// third fewer bytes from L2: the leader's MMA thread now waits for the slower of two TMA streams plus a remote
+// mbarrier arrive per stage (the peer's forwarder), and both CTAs' epilogues gate the accumulator hand-back.  The
+// single-CTA kernel's 0.59 of tensor peak is therefore not simply the L2 -> SM byte rate.  Default off.  The
+// packed-weight format differs between the two, so packing and launching consult the same switch.
+bool mlp_chain_pair() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("O4D_CHAIN_PAIR");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
+
+int mlp_chain_pack_launch(const float* W, int64_t n, int64_t k, int64_t ldw, void* packed, cudaStream_t st) {
+    return mlp_chain_pair() ? tc_pack_pair_launch(W, n, k, ldw, packed, st) : tc_pack_launch(W, n, k, ldw, packed, st);
+}
+
+// images are sized for an EVEN number of row tiles: the pair kernel always processes tiles two at a time
 size_t act_image_bytes(int64_t rows, int cols) {
-    return (size_t)cdiv(rows, mc::BM) * (size_t)cdiv(cols, 32) * mc::IMG_CHUNK_BYTES;
+    return (size_t)(cdiv(cdiv(rows, mc::BM), 2) * 2) * (size_t)cdiv(cols, 32) * mc::IMG_CHUNK_BYTES;
 }
 
 int act_image_launch(const float* src, int64_t ld, int64_t rows, int cols, int relu, void* img, cudaStream_t st) {
@@ -447,11 +530,32 @@ int mlp_chain_launch(mc::Program& prog, cudaStream_t st) {
         op.n_img = op.img ? op.img_cpt * 32 : 0;
         flops += 2.0 * (double)prog.rows * op.k_alg * op.n;
     }
-    O4D_SMEM_ATTR(mc::mlp_chain_kernel, mc::SMEM_BYTES);
+    ProfScope prof(PROF_LINEAR, flops, st);
+    if (mlp_chain_pair()) {
+        for (int o = 0; o < prog.nops; ++o)
+            O4D_REQUIRE(prog.op[o].bn % 16 == 0, "mlp chain: pair kernel needs n-tiles in multiples of 16");
+        O4D_SMEM_ATTR(mc::mlp_chain_kernel<true>, mc::SMEM_BYTES);
+        const int tile_pairs = (prog.tiles + 1) / 2;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(2 * (tile_pairs < 74 ? tile_pairs : 74)), 1, 1);
+        cfg.blockDim = dim3(mc::THREADS, 1, 1);
+        cfg.dynamicSmemBytes = mc::SMEM_BYTES;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        O4D_CUDA(cudaLaunchKernelEx(&cfg, mc::mlp_chain_kernel<true>, prog));
+        count_launch();
+        return 0;
+    }
+    O4D_SMEM_ATTR(mc::mlp_chain_kernel<false>, mc::SMEM_BYTES);
     int grid = 148;
     if (prog.tiles < grid) grid = prog.tiles;
-    ProfScope prof(PROF_LINEAR, flops, st);
-    mc::mlp_chain_kernel<<<grid, mc::THREADS, mc::SMEM_BYTES, st>>>(prog);
+    mc::mlp_chain_kernel<false><<<grid, mc::THREADS, mc::SMEM_BYTES, st>>>(prog);
     O4D_LAUNCH_CHECK();
     return 0;
 }
@@ -505,8 +609,8 @@ extern "C" int o4d_resblock_forward_f32(const float* x, int64_t rows, int d, int
         set_error("resblock: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
         return O4D_E_WORKSPACE;
     }
-    O4D_TRY(tc_pack_launch(w0, d_hidden, d, d, w.w0p, st));
-    O4D_TRY(tc_pack_launch(w1, d, d_hidden, d_hidden, w.w1p, st));
+    O4D_TRY(mlp_chain_pack_launch(w0, d_hidden, d, d, w.w0p, st));
+    O4D_TRY(mlp_chain_pack_launch(w1, d, d_hidden, d_hidden, w.w1p, st));
     O4D_TRY(act_image_launch(x, ldx, rows, d, 1, w.img_x, st));                 // implicit.py:93  act(x)
     mc::Program prog;
     prog.nops = 2;

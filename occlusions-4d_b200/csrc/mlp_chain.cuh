@@ -44,5 +44,8 @@ int act_image_launch(const float* src, int64_t ld, int64_t rows, int cols, int r
 bool mlp_chain_layer_ok(int64_t k_total, int64_t n);
 void mlp_chain_tiling(int64_t n, int* bn_out, int* ntiles_out);
 int mlp_chain_launch(mc::Program& prog, cudaStream_t st);
+bool mlp_chain_pair();
+// packs a weight in the format the chain kernel of this process reads (single-CTA or pair)
+int mlp_chain_pack_launch(const float* W, int64_t n, int64_t k, int64_t ldw, void* packed, cudaStream_t st);
 
 }  // namespace o4d

@@ -142,6 +142,8 @@ int linear_tc_launch(const float* A, int64_t rows, int64_t k, int64_t lda, const
 // fp32 weight pointer they were packed from.
 size_t tc_pack_bytes(int64_t n, int64_t k);
 int tc_pack_launch(const float* W, int64_t n, int64_t k, int64_t ldw, void* packed, cudaStream_t st);
+// same bytes, pair format of the fused multi-layer kernel (cta_group::2: each CTA of a pair copies half of a slab)
+int tc_pack_pair_launch(const float* W, int64_t n, int64_t k, int64_t ldw, void* packed, cudaStream_t st);
 bool tc_shape_ok(int64_t rows, int64_t k, int64_t n);
 int linear_tc_packed_launch(const float* A, int64_t rows, int64_t k, int64_t lda, const void* packed, int64_t n,
                             const float* bias, const float* R, int64_t ldr, float* C, int64_t ldc, int flags,
@@ -151,6 +153,7 @@ struct PackedSet {
     const float* key[CAP];
     const void* packed[CAP];
     int count = 0;
+    bool pair = false;   // packed in the pair format of the fused multi-layer kernel: not readable by the per-layer kernel
     void add(const float* w, const void* p) {
         if (count < CAP) { key[count] = w; packed[count] = p; ++count; }
     }

@@ -66,6 +66,7 @@ __device__ __forceinline__ uint32_t umma_idesc(int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
+
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -95,6 +96,60 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
     lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
 
+// ---- CTA pairs (cluster of two, tcgen05 cta_group::2): the leader CTA (cluster rank 0) issues M = 256 MMAs whose rows
+// 0-127 accumulate in its own tensor memory and rows 128-255 in the peer's; each CTA supplies its own A rows and HALF
+// of the B rows from its shared memory.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t local_addr, uint32_t rank) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(rank));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cl(uint32_t a, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(a), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// wait with cluster-scope acquire (arrivals come from the peer CTA or from a multicast tcgen05.commit)
+__device__ __forceinline__ void mbar_wait_cl(uint32_t a, uint32_t parity) {
+    if (mbar_try_wait_cl(a, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait_cl(a, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ uint32_t umma_idesc_pair(int n) {          // M = 256 across the pair
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives on the mbarrier at this offset in BOTH CTAs of the pair once the MMAs issued so far have retired
+__device__ __forceinline__ void umma_commit_pair(uint32_t mbar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(mbar),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
 
 }  // namespace tch
 }  // namespace o4d

@@ -9,7 +9,8 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(os.path.dirname(_HERE), 'csrc')
-LIB_PATH = os.path.join(_HERE, 'libo4d.so')
+# O4D_LIB selects another build of the same library (e.g. the cycle-stamp build `make STAMPS=1 OUT=... BUILD=...`)
+LIB_PATH = os.environ.get('O4D_LIB') or os.path.join(_HERE, 'libo4d.so')
 
 c_i64 = ctypes.c_int64
 c_int = ctypes.c_int

@@ -20,7 +20,7 @@ for which in ('greater', 'carla'):
     q, a, g = ck['query'].cuda(), ck['abstract'].cuda(), ck['glob'].cuda()
     qbig = q.repeat(8, 1)
     row = {'ref_fp32_vs_fp64': float((ck['out'].double() - ck['out64']).abs().max() / ck['out64'].abs().max())}
-    for name, prec, mode in (('fp32_cuda_cores', 0, 1), ('bf16x3', 1, 1), ('drop_hiddenhi_x_Wlo', 1, 2),
+    for name, prec, mode in (('fp32_cuda_cores', 0, 1), ('bf16x3_all_three_products', 1, 1), ('default_logits_W_bf16', 1, 2),
                              ('drop_hiddenlo_x_Whi', 1, 3), ('bf16_single_pass', 2, 1)):
         dec.o4d_precision = prec
         h.o4d_debug_set_fused_passes(mode)
@@ -34,6 +34,6 @@ for which in ('greater', 'carla'):
         e = float((out.cpu().double() - ck['out64']).abs().max() / ck['out64'].abs().max())
         ep = float((pen.cpu()[:, :16].double() - ck['penult64']).abs().max() / ck['penult64'].abs().max())
         row[name] = {'out_vs_fp64': e, 'penult_vs_fp64': ep, 'ms_65536_queries': dt * 1e3}
-    h.o4d_debug_set_fused_passes(1)
+    h.o4d_debug_set_fused_passes(0)       # back to the library default
     res[which] = row
 print(json.dumps(res, indent=1))

@@ -16,8 +16,9 @@ z = np.load(os.path.join(ROOT, 'tests', 'golden', 'c2_greater_seeded.npz'))
 abstract, glob = torch.from_numpy(z['abstract']).to(dev), torch.from_numpy(z['glob']).to(dev)
 q = configs.synthetic_queries(cfg)[:32768].contiguous().to(dev)
 h = ctypes.CDLL(_lib.LIB_PATH)
-for prec in (1, 2):
+for prec, mode in ((1, 1), (1, 2), (2, 1)):
     dec.o4d_precision = prec
+    h.o4d_debug_set_fused_passes(mode)
     with torch.no_grad():
         scene = dec.o4d_scene(abstract, glob)
         dcfg, dparams = dec.o4d_config(), dec.o4d_params()
@@ -32,6 +33,6 @@ for prec in (1, 2):
         e1.record(); torch.cuda.synchronize()
     buf=(ctypes.c_longlong*16)()
     h.o4d_debug_read(buf); v=list(buf)
-    print('prec %d: %.3f ms/batch; fused stamps: start->loop %d, loop %d, loop_end->acc2 %d, epilogue %d, total %d' % (prec, e0.elapsed_time(e1)/5, v[0]-v[4], v[1]-v[0], v[2]-v[1], v[3]-v[2], v[3]-v[4])); print('   epilogue parts: acc1 wait %d, stage %d, barriers %d, reduce %d, issue_v %d' % (v[5],v[6],v[7],v[8],v[9]))
-    h.o4d_debug_read_tc(buf); v=list(buf)
+    print('prec %d mode %d: %.3f ms/batch; fused stamps: start->loop %d, loop %d, loop_end->acc2 %d, epilogue %d, total %d' % (prec, mode, e0.elapsed_time(e1)/5, v[0]-v[4], v[1]-v[0], v[2]-v[1], v[3]-v[2], v[3]-v[4])); print('   epilogue parts: acc1 wait %d, stage %d, barriers %d, reduce %d, issue_v %d' % (v[5],v[6],v[7],v[8],v[9]))
+    h.o4d_debug_read_tc(buf); v=list(buf)  # per-layer kernel (not on the chain path)
     print('   linear stamps: loop %d, wait accum %d, epilogue %d' % (v[1]-v[0], v[2]-v[1], v[3]-v[2]))

@@ -558,21 +558,18 @@ def sampler_and_loss_timing(dev):
 def train_step_bench(dev, world, rank, steps):
     """BASELINE.json configs[4] per GPU: one CARLA-4D sample (14336 points), 4 frames x 17,203 query
     points (args.py:254,257 / train.py:270-274), forward + backward through the nn.Module API
-    (o4d/autograd.py -> backward kernels), gradient averaging over ranks, AdamW.  The loss heads and the
-    optimizer are the caller's torch code (out of scope); the query sampler is
-    excluded.  Returns a dict for the bench line."""
+    (o4d/autograd.py -> backward kernels), the fused loss heads (o4d.loss), gradient averaging over
+    ranks, AdamW (the caller's torch optimizer, out of scope); the query sampler is excluded.  Timed twice: bf16x3
+    operands (fp32-grade, what the parity tests check) and single-pass bf16 operands with fp32 accumulation and fp32
+    master weights -- the "bf16" of BASELINE.json's config (the reference's mixed_precision = torch autocast).
+    Returns a dict for the bench line."""
     import torch.distributed as dist
-    from o4d import parallel
+    from o4d import loss as o4d_loss, parallel
     from tests import configs
     cfg = configs.C3_CARLA
-    enc, dec = configs.build_modules(cfg, dev)
-    enc.train()
-    dec.train()
-    params = list(enc.parameters()) + list(dec.parameters())
-    opt = torch.optim.AdamW(params, lr=1e-4)
+    frames, per_frame = 4, 17203
     g = torch.Generator().manual_seed(1830 + rank)
     pcl = configs.synthetic_cloud(cfg).to(dev)
-    frames, per_frame = 4, 17203
     lo = torch.tensor([0.0, -16.0, -1.0])
     hi = torch.tensor([40.0, 16.0, 6.4])
     queries = []
@@ -581,47 +578,76 @@ def train_step_bench(dev, world, rank, steps):
         q[:, :3] = q[:, :3] * (hi - lo) + lo
         q[:, 3] = float(f)
         queries.append(q.to(dev))
-    target = torch.rand(frames, per_frame, 6, generator=g).to(dev)
+    # targets (B, n, 6) as pipeline.py:184 shapes them: density, RGB, mark_track, semantic tag
+    target = torch.rand(frames, per_frame, 6, generator=g)
+    target[..., 0] = (target[..., 0] > 0.5).float()
+    target[..., 4] = 0.0
+    target[..., 5] = torch.randint(0, 13, (frames, per_frame), generator=g).float()
+    target = target.to(dev)
+    weights = torch.tensor([1.0, 1.0, 0.6, 1.0], device=dev)        # color, density, segmentation, tracking
 
-    def step():
-        opt.zero_grad(set_to_none=True)
-        abstract, glob, _ = enc(pcl[None], False)
-        total = 0.0
-        for f in range(frames):
-            out, _ = dec(queries[f], abstract[0], glob[0], None)
-            t = target[f]
-            loss = torch.nn.functional.binary_cross_entropy_with_logits(out[:, 0], (t[:, 0] > 0.5).float()) + \
-                (out[:, 1:4] - t[:, 1:4]).abs().mean() + \
-                torch.nn.functional.cross_entropy(out[:, 5:18], (t[:, 5] * 12.99).long())
-            total = total + loss
-        (total / frames).backward()
+    def run(precision):
+        enc, dec = configs.build_modules(cfg, dev)
+        enc.train()
+        dec.train()
+        enc.o4d_precision = dec.o4d_precision = precision
+        for m in list(enc.modules()) + list(dec.modules()):
+            if hasattr(m, 'o4d_precision'):
+                m.o4d_precision = precision
+        params = list(enc.parameters()) + list(dec.parameters())
+        opt = torch.optim.AdamW(params, lr=1e-4)
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            abstract, glob, _ = enc(pcl[None], False)
+            total = 0.0
+            for f in range(frames):
+                out, _ = dec(queries[f], abstract[0], glob[0], None)
+                heads = o4d_loss.implicit_loss_heads(out, target[f], 'rgb', 13, True)
+                total = total + (heads * weights).sum()
+            (total / frames).backward()
+            if world > 1:
+                parallel.allreduce_gradients([enc, dec])
+            opt.step()
+            return total
+
+        step()                                   # warm-up (workspaces, allocator)
+        torch.cuda.synchronize()
         if world > 1:
-            parallel.allreduce_gradients([enc, dec])
-        opt.step()
-        return total
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            total = step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        loss = float(total.detach()) / frames
+        del opt, enc, dec
+        torch.cuda.empty_cache()
+        return ms, loss
 
-    step()                                   # warm-up (workspaces, allocator)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        total = step()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    del opt
+    ms, loss = run(1)
+    ms_bf16, loss_bf16 = run(2)
     extras = sampler_and_loss_timing(dev) if rank == 0 else None
+    flop = 3.0 * frames * per_frame * 47.9e6                      # ~3x the forward, 9.9 TFLOP per sample
+    peak, _ = measured_peak()
     return {'sampler_and_loss_heads': extras, 'ms_per_step': ms, 'samples_per_step': world, 'queries_per_sample': frames * per_frame,
             'points_per_sample': cfg['n_points'], 'query_grads_per_s': world * frames * per_frame / (ms / 1e3),
-            'loss': float(total.detach()) / frames, 'steps': steps, 'precision': 'bf16x3 (fp32-grade) forward and backward',
-            'what': 'CARLA config 5 shape: encoder + 4 decoder frames forward/backward, grad all-reduce, AdamW; '
-                    'sampler excluded'}
+            'loss': loss, 'steps': steps, 'precision': 'bf16x3 (fp32-grade) forward and backward',
+            'bf16': {'ms_per_step': ms_bf16, 'query_grads_per_s': world * frames * per_frame / (ms_bf16 / 1e3), 'loss': loss_bf16,
+                     'precision': 'single-pass bf16 operands, fp32 accumulation, fp32 master weights (BASELINE config 5 "bf16")',
+                     'roofline': {'bound': 'tensor', 'achieved': flop / (ms_bf16 / 1e3) / 1e12, 'peak': peak, 'unit': 'TFLOP/s',
+                                  'frac': flop / (ms_bf16 / 1e3) / 1e12 / peak}},
+            'roofline': {'bound': 'tensor', 'achieved': flop / (ms / 1e3) / 1e12, 'peak': peak, 'unit': 'TFLOP/s',
+                         'frac': flop / (ms / 1e3) / 1e12 / peak,
+                         'note': 'algorithmic flops of the step (3 x forward, SURVEY 8d) over the whole step time'},
+            'what': 'CARLA config 5 shape: encoder + 4 decoder frames forward/backward, fused loss heads, grad all-reduce, '
+                    'AdamW; sampler excluded'}
 
 
 def run_o4d(args):

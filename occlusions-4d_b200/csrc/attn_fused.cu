@@ -22,8 +22,9 @@
 // slices through cooperative cp.async into two gather stages.  All contractions use the bf16x3
 // split (hi*hi + lo*hi + hi*lo, fp32 accumulate) unless `split` is 0.
 //
-// Warps: 0-7 row warps (TMEM lane quarter w & 3, column half w >> 2), 8 weight stream (and ninth
-// reduce warp of the softmax epilogue), 9 MMA2 issuer, 10 MMA1 / delta issuer.
+// Warps: 0-15 row warps = two groups of eight (TMEM lane quarter w & 3, column half (w >> 2) & 1, group w >> 3) that
+// convert ALTERNATE hidden chunks, 16 weight stream, 17 MMA2 issuer (both join the softmax reduce of the epilogue),
+// 18 MMA1 / delta issuer.
 // TMEM: columns [0, d) logits, [416, 512) the three acc1 / hidden buffers.  One CTA per SM.
 // How the kernel got here (what bound it at each step, measured): DESIGN.md section 4.
 #include "o4d_common.cuh"
@@ -35,8 +36,11 @@ namespace fa {
 
 constexpr int BM = 128;
 constexpr int HC = 32;          // hidden units per chunk == K of the second contraction per chunk
-constexpr int ROW_WARPS = 8;    // two warps per TMEM lane quarter
-constexpr int THREADS = (ROW_WARPS + 3) * 32;   // 8 row warps, weight-stream warp, MMA2 issuer, MMA1 / delta issuer
+constexpr int GROUP_WARPS = 8;  // one conversion group: two warps per TMEM lane quarter
+constexpr int ROW_GROUPS = 2;   // groups convert alternate hidden chunks (chunk c belongs to group c & 1)
+constexpr int ROW_WARPS = GROUP_WARPS * ROW_GROUPS;
+constexpr int ROW_THREADS = ROW_WARPS * 32;
+constexpr int THREADS = (ROW_WARPS + 3) * 32;   // 16 row warps, weight-stream warp, MMA2 issuer, MMA1 / delta issuer
 constexpr int R_BYTES = BM * 32 * 2;         // one bf16 image of a (128 x 32) A operand
 constexpr int NBUF = 3;                      // acc1 (TMEM) / hidden A2 (smem) buffers: MMA1 runs two chunks ahead
 constexpr int WC_STAGES = 4;                 // ring of Wc chunks (4 KB each)
@@ -56,8 +60,9 @@ constexpr int STG_LD = 33;                   // padded row pitch (floats) of the
 constexpr int G_PITCH = 144;
 constexpr int G_ROWS = BM + 16;              // 128 Ka rows + up to 16 Qa rows (k >= 8)
 constexpr int G_STAGE = G_ROWS * G_PITCH;    // 20,736 B
-constexpr int G_STAGES = 2;
-constexpr int TAIL_BYTES = 256 + BM * 4;     // mbarriers + TMEM slot, then the tile's neighbour ids
+constexpr int G_STAGES = 2;                  // per group; group 1's pair lives in the (idle during the main loop) hidden-buffer region
+constexpr int BAR_BYTES = 320;               // 34 mbarriers + the TMEM slot
+constexpr int TAIL_BYTES = BAR_BYTES + BM * 4;   // then the tile's neighbour ids
 
 __host__ __device__ inline int w2_bytes(int d) { return 2 * d * 32 * 2; }             // W_a2 chunk, hi + lo
 __host__ __device__ inline int wstage_bytes(int d) { return 2 * WC_BYTES + w2_bytes(d); }  // packed chunk in HBM
@@ -197,7 +202,9 @@ __device__ __forceinline__ void store_a_half_row(uint8_t* hi_img, uint8_t* lo_im
 
 __device__ long long g_dbg[16];   // cycle stamps of one tile (diagnostics, read by o4d_debug_read)
 
-constexpr int EPI_WARPS = ROW_WARPS + 1;     // the weight-stream warp helps with the softmax reduce
+constexpr int EPI_WARPS = ROW_WARPS + 2;     // the weight-stream warp and the MMA2 warp join the softmax reduce
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+static_assert(G_STAGES * G_STAGE <= NBUF * 2 * R_BYTES, "group 1's gather stages must fit the idle hidden-buffer region");
 constexpr int EPI_GROUP = 2;                 // chunks staged per barrier pair
 
 // Per-channel softmax over a query's k staged rows and the weighted sum of (V + delta):
@@ -208,22 +215,30 @@ __device__ __forceinline__ void reduce_task(const float* tile_l, const float* ti
     constexpr int KV = KT ? KT : O4D_MAX_K;
     const float* lq = tile_l + (q * k) * STG_LD + lane;
     const float* vq = tile_v + (q * k) * STG_LD + lane;
-    float lgt[KV];
-    float mx = -3.4e38f;
+    // Four independent accumulation chains (j = 0, 4, 8, ... / 1, 5, ... / ...): the serial max -> exp -> sum chain over
+    // 14 neighbours ran at an IPC of ~0.4 with 4.5 warps per scheduler (in-kernel counters: 8 k cycles of reduce per tile).
+    float lgt[KV], val[KV];
+    float m4[4] = {-3.4e38f, -3.4e38f, -3.4e38f, -3.4e38f};
 #pragma unroll
     for (int jj = 0; jj < KV; ++jj)
         if (jj < k) {
             lgt[jj] = lq[jj * STG_LD];
-            mx = fmaxf(mx, lgt[jj]);
+            val[jj] = vq[jj * STG_LD];
+            m4[jj & 3] = fmaxf(m4[jj & 3], lgt[jj]);
         }
-    float den = 0.f, num = 0.f;
+    const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+    float d4[4] = {0.f, 0.f, 0.f, 0.f}, n4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int jj = 0; jj < KV; ++jj)
         if (jj < k) {
             const float w = ex2_approx(lgt[jj] - mx);
-            den += w;
-            num = fmaf(w, vq[jj * STG_LD], num);
+            d4[jj & 3] += w;
+            n4[jj & 3] = fmaf(w, val[jj], n4[jj & 3]);
         }
+    const float den = (d4[0] + d4[1]) + (d4[2] + d4[3]);
+    const float num = (n4[0] + n4[1]) + (n4[2] + n4[3]);
+    // (Writing the bf16 hi / lo activation image of the next layer from here -- 4-byte stores scattered over the image --
+    // was measured: +1.0 ms per step in this reduce against 0.9 ms for the separate conversion pass it saves.  Not kept.)
     out_row[lane] = __fdividef(num, den) + bias[lane];
 }
 
@@ -241,6 +256,7 @@ struct Params {
     float* out;                            // (n, d)
     int64_t n;
     int d, k, tq, split;
+    int issue_mode;                        // MMA1(c) waits for MMA2(c - 3): 1 = to be issued (default), 0 = to complete
     float scale_log2;                      // log2(e) / sqrt(d): softmax evaluated with exp2
 };
 
@@ -258,9 +274,9 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fused_kernel(const Params p) 
     const int OFF_G = off_g(d);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_G + G_STAGES * G_STAGE);
     enum { W_FULL = 0, W_EMPTY = 2, WC_FULL = 4, WC_EMPTY = 8, ACC1_FULL = 12, A2_FULL = 15, A2_EMPTY = 18,
-           R_READY = 21, ACC2_FULL = 22, G_FULL = 23, G_EMPTY = 25, NBARS = 27 };
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
-    int32_t* s_j = reinterpret_cast<int32_t*>(smem + OFF_G + G_STAGES * G_STAGE + 256);   // neighbour id per tile row
+           R_READY = 21, ACC2_FULL = 22, G_FULL = 23, G_EMPTY = 27, A2_ISSUED = 31, NBARS = 34 };   // G_*: [group][stage]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBARS);
+    int32_t* s_j = reinterpret_cast<int32_t*>(smem + OFF_G + G_STAGES * G_STAGE + BAR_BYTES);   // neighbour id per tile row
     const uint32_t bar0 = smem_u32(bars);
 #define BAR(i) (bar0 + 8u * (uint32_t)(i))
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -272,14 +288,15 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fused_kernel(const Params p) 
         for (int i = 0; i < WC_STAGES; ++i) { mbar_init(BAR(WC_FULL + i), 1); mbar_init(BAR(WC_EMPTY + i), 1); }
         for (int i = 0; i < NBUF; ++i) {
             mbar_init(BAR(ACC1_FULL + i), 1);
-            mbar_init(BAR(A2_FULL + i), ROW_WARPS);
+            mbar_init(BAR(A2_FULL + i), GROUP_WARPS);     // a chunk is converted (or drained) by ONE group
             mbar_init(BAR(A2_EMPTY + i), 1);
+            mbar_init(BAR(A2_ISSUED + i), 1);
         }
-        mbar_init(BAR(R_READY), ROW_WARPS);
+        mbar_init(BAR(R_READY), GROUP_WARPS);             // group 0 builds the r operand
         mbar_init(BAR(ACC2_FULL), 1);
-        for (int i = 0; i < G_STAGES; ++i) {
-            mbar_init(BAR(G_FULL + i), ROW_WARPS * 32);   // one cp.async-completion arrival per row thread
-            mbar_init(BAR(G_EMPTY + i), ROW_WARPS);       // one arrival per row warp after its reads
+        for (int i = 0; i < ROW_GROUPS * G_STAGES; ++i) {
+            mbar_init(BAR(G_FULL + i), GROUP_WARPS * 32);   // one cp.async-completion arrival per thread of the group
+            mbar_init(BAR(G_EMPTY + i), GROUP_WARPS);       // one arrival per warp of the group after its reads
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -293,25 +310,43 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fused_kernel(const Params p) 
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // epilogue staging tiles (see the row warps' epilogue): 3 over the hidden buffers / Wc ring, 1 over W stage 1
+    // epilogue staging tiles (see the epilogue): 3 over the hidden-buffer region / Wc ring, 1 over W stage 1
     constexpr int TILE_B = BM * STG_LD * 4;
     auto tile_ptr = [&](int t) -> float* {
         return reinterpret_cast<float*>(t < 3 ? smem + OFF_A2 + t * TILE_B : smem + OFF_W + w2);
     };
 
-    if (warp < ROW_WARPS) {
-        // ================================================================== row warps
-        // Two warps per TMEM lane quarter: thread (r, half) owns tile row r and columns
-        // [16*half, 16*half+16) of every 32-column chunk.
-        const int r = threadIdx.x & (BM - 1);            // tile row == TMEM lane
-        const int half = threadIdx.x >> 7;
+    // ---- geometry of a row thread.  Two GROUPS of eight warps; inside a group two warps per TMEM lane quarter: thread
+    // (r, half) owns tile row r and columns [16*half, 16*half+16) of every 32-column chunk its group converts; group g
+    // converts the hidden chunks c = g, g + 2, ...  Three things bound the main loop at about the same level (in-kernel
+    // stamps): the L2 -> SM stream of W_a2 (57 KB per chunk with hi + lo images), the tensor pipe
+    // (1.25 k cycles of MMA2 per chunk with three passes) and the per-chunk chain wait -> tmem ld -> add / ReLU / split
+    // -> tmem st -> arrive of ONE group (~1.2 k).  With the two-pass logits contraction (split 2: half the stream, two
+    // thirds of the MMAs) the conversion chain is what is left, so two groups take alternate chunks.  (Splitting a
+    // chunk's 32 columns over four warps instead does NOT work: the hi / lo images of a K=16 step interleave in
+    // 8-column blocks, so a warp's stores would overwrite accumulator columns another warp has not read yet.)
+    // The two reduce-only warps of the epilogue evaluate the same expressions (unused there).
+    const bool is_row = warp < ROW_WARPS;
+    const int r = threadIdx.x & (BM - 1);            // tile row == TMEM lane
+    const int half = (threadIdx.x >> 7) & 1;
+    const int grp = (threadIdx.x >> 8) & 1;          // conversion group
+    const int gwarp = warp & (GROUP_WARPS - 1);      // warp index inside the group
+    const int64_t q0 = (int64_t)blockIdx.x * p.tq;
+    const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    // gather staging (see G_PITCH): a warp copies 16 Ka rows and up to 2 Qa rows per chunk of its group
+    const int g_piece = lane & 7, g_sub = lane >> 3;
+    const int g_rbase = (gwarp & 3) * 32 + (gwarp >> 2) * 16;
+    int gj[4] = {0, 0, 0, 0};
+    const bool dbg = O4D_STAMPS && (blockIdx.x == gridDim.x / 2) && threadIdx.x == 0;
+
+    if (is_row) {
+        // ================================================================== row warps: prologue + main loop
         const int qi = r / k, jn = r - qi * k;
-        const int64_t q0 = (int64_t)blockIdx.x * p.tq;
         const int64_t i = q0 + qi;
         const bool valid = (qi < p.tq) && (i < p.n);
         const int j = valid ? p.nbr[i * k + jn] : 0;
-        if (half == 0) s_j[r] = j;
-        {
+        if (half == 0 && grp == 0) s_j[r] = j;
+        if (grp == 0) {
             float rv[16];
             if (valid) {
                 const float rx = p.pos[i * p.ldpos + 0] - p.pos2[(int64_t)j * p.ldpos2 + 0];
@@ -332,50 +367,55 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fused_kernel(const Params p) 
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(R_READY));
         }
-        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-        // ---- gather staging (see G_PITCH): this warp copies 16 Ka rows and up to 2 Qa rows per chunk
-        asm volatile("barrier.sync 1, 256;" ::: "memory");                 // s_j complete
-        const int g_piece = lane & 7, g_sub = lane >> 3;
-        const int g_rbase = (warp & 3) * 32 + (warp >> 2) * 16;
-        int gj[4];
+        __syncwarp();
+        asm volatile("bar.sync 1, %0;" ::"n"(ROW_THREADS) : "memory");      // s_j complete
 #pragma unroll
         for (int it = 0; it < 4; ++it) gj[it] = s_j[g_rbase + it * 4 + g_sub];
-        const int g_qi = warp * 2 + g_sub;                              // Qa row handled by lanes 0-15
+        const int g_qi = gwarp * 2 + g_sub;                             // Qa row handled by lanes 0-15
         const bool g_has_q = lane < 16 && g_qi < p.tq;
         const int64_t g_qrow = min(q0 + (int64_t)g_qi, p.n - 1);
-        auto issue_gather = [&](int cn) {
-            const uint32_t gst = smem_base + OFF_G + (cn & 1) * G_STAGE;
+        // gather stages of this group: group 0 behind the weight stages, group 1 over the hidden-buffer region (idle
+        // until the epilogue turns it into staging tiles)
+        const uint32_t g_region = grp == 0 ? (uint32_t)OFF_G : (uint32_t)OFF_A2;
+        const int gbar = grp * G_STAGES;                                // this group's G_FULL / G_EMPTY barriers
+        auto issue_gather = [&](int cn) {                               // cn: a chunk of THIS group, stage (cn >> 1) & 1
+            const uint32_t gst = smem_base + g_region + ((cn >> 1) & 1) * G_STAGE;
 #pragma unroll
             for (int it = 0; it < 4; ++it)
                 cp_async16(gst + (g_rbase + it * 4 + g_sub) * G_PITCH + g_piece * 16,
                            p.ka + (int64_t)gj[it] * 2 * d + cn * HC + g_piece * 4);
             if (g_has_q)
                 cp_async16(gst + (BM + g_qi) * G_PITCH + g_piece * 16, p.qa + g_qrow * 2 * d + cn * HC + g_piece * 4);
-            cp_async_mbar_arrive_noinc(BAR(G_FULL + (cn & 1)));
+            cp_async_mbar_arrive_noinc(BAR(G_FULL + gbar + ((cn >> 1) & 1)));
         };
-        issue_gather(0);
+        if (grp < NC) issue_gather(grp);
         const int qi_rd = min(qi, p.tq - 1);                            // padding rows read a real query's slice
-        const uint32_t rd_k = OFF_G + r * G_PITCH + half * 64;
-        const uint32_t rd_q = OFF_G + (BM + qi_rd) * G_PITCH + half * 64;
-        const bool dbg = O4D_STAMPS && (blockIdx.x == gridDim.x / 2) && threadIdx.x == 0;
+        const uint32_t rd_k = g_region + r * G_PITCH + half * 64;
+        const uint32_t rd_q = g_region + (BM + qi_rd) * G_PITCH + half * 64;
         if (dbg) g_dbg[0] = clock64();
-        for (int c = 0; c < NC; ++c) {
+        long long s_top = 0, s_acc1 = 0, s_ld = 0, s_cvt = 0, s_st = 0, ts = 0;
+        for (int c = grp; c < NC; c += ROW_GROUPS) {
+            if (dbg) ts = clock64();
             const int b = c % NBUF;
             const uint32_t use = (uint32_t)(c / NBUF);
-            if (c + 1 < NC) {
-                // stage (c+1)&1 was last read for chunk c-1: every row warp must have released it
-                const uint32_t gu = (uint32_t)((c + 1) >> 1);
-                if (gu > 0) mbar_wait(BAR(G_EMPTY + ((c + 1) & 1)), (gu - 1u) & 1u);
-                issue_gather(c + 1);
+            const int gi = c >> 1;                       // running index of the chunk inside this group
+            const int gs_idx = gi & 1;                   // gather stage of chunk c
+            if (c + ROW_GROUPS < NC) {
+                // the other stage of this group was last read for the group's previous chunk (gi - 1): every warp of
+                // the group must have released it
+                if (gi > 0) mbar_wait(BAR(G_EMPTY + gbar + (gs_idx ^ 1)), (uint32_t)((gi - 1) >> 1) & 1u);
+                issue_gather(c + ROW_GROUPS);
             }
+            if (dbg) { const long long t1 = clock64(); s_top += t1 - ts; ts = t1; }
             mbar_wait(BAR(ACC1_FULL + b), use & 1u);
             tc_fence_after();
+            if (dbg) { const long long t1 = clock64(); s_acc1 += t1 - ts; ts = t1; }
             uint32_t acc[16];
             tmem_ld16_nowait(taddr + ACC1_COL + b * 32 + half * 16, acc);
-            mbar_wait(BAR(G_FULL + (c & 1)), (uint32_t)(c >> 1) & 1u);
+            mbar_wait(BAR(G_FULL + gbar + gs_idx), (uint32_t)(gi >> 1) & 1u);
             float qk[16];
             {
-                const uint8_t* gs = smem + (c & 1) * G_STAGE;
+                const uint8_t* gs = smem + gs_idx * G_STAGE;
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const float4 qv = *reinterpret_cast<const float4*>(gs + rd_q + 16 * e);
@@ -385,17 +425,18 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fused_kernel(const Params p) 
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(BAR(G_EMPTY + (c & 1)));        // this warp's reads of the stage are done
+            if (lane == 0) mbar_arrive(BAR(G_EMPTY + gbar + gs_idx));   // this warp's reads of the stage are done
             tmem_ld_wait();
+            if (dbg) { const long long t1 = clock64(); s_ld += t1 - ts; ts = t1; }
             float h[16];
 #pragma unroll
             for (int e = 0; e < 16; ++e) h[e] = fmaxf(__uint_as_float(acc[e]) + qk[e], 0.f);
             // The hidden chunk goes back into the SAME tensor-memory columns acc1[b] came from, as the A
             // operand of MMA2 (bf16 hi / lo, two values per 32-bit column): this thread read columns
             // [16*half, 16*half+16) of the buffer and overwrites them with [hi (8 columns) | lo (8 columns)]
-            // of its 16 hidden units = one K=16 step.  The main loop was shared-memory-bandwidth bound
-            // (~239 KB per chunk at 128 B/cycle: every one of the 12 MMA2 instructions re-read a 4 KB A
-            // slab plus 6.6 KB of weights); A from TMEM removes 49 KB of reads and 16 KB of stores per chunk.
+            // of its 16 hidden units = one K=16 step.  (With the hidden chunk in shared memory the loop was
+            // shared-memory-bandwidth bound: every one of the 12 MMA2 instructions re-read a 4 KB A slab plus
+            // 6.6 KB of weights; A from TMEM removed 49 KB of reads and 16 KB of stores per chunk.)
             // No "buffer empty" wait: ACC1_FULL(c) means MMA1(c) has retired, and the tensor pipe runs in
             // issue order, so MMA2(c - NBUF), the last reader of these columns, retired before it.
             {
@@ -409,6 +450,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fused_kernel(const Params p) 
                     wlo[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
                 }
                 const uint32_t ta = taddr + ACC1_COL + b * 32 + half * 16;
+                if (dbg) { const long long t1 = clock64(); s_cvt += t1 - ts; ts = t1; }
                 tmem_st8(ta, whi);
                 tmem_st8(ta + 8, wlo);
                 tmem_st_wait();
@@ -416,104 +458,9 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fused_kernel(const Params p) 
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(A2_FULL + b));
+            if (dbg) { const long long t1 = clock64(); s_st += t1 - ts; ts = t1; }
         }
-        // ------------------------------------------------ softmax / aggregation epilogue
-        if (dbg) g_dbg[1] = clock64();
-        mbar_wait(BAR(ACC2_FULL), 0);
-        tc_fence_after();
-        if (dbg) g_dbg[2] = clock64();
-        // Staging tiles [row][33] of one 32-channel chunk (padding: conflict-free row-wise stores and
-        // column-wise loads): logits * scale and V + delta, 16.5 KB each.  The per-channel softmax over a
-        // query's k rows is a reduction ACROSS TMEM lanes, so it goes through shared memory.  Chunks are
-        // processed in groups of two (4 tiles: 3 over the idle hidden buffers / Wc ring, 1 over the idle W
-        // stage 1; W_p2 sits in W stage 0): 18 (chunk, query) tasks dealt round-robin to the 8 warps.
-        // The V_j slices of a group are fetched one group ahead into the two (now idle) gather stages by
-        // the same cooperative cp.async pattern as Ka in the main loop: a row-per-thread gather from global
-        // costs one L1 wavefront per lane (~1000 LSU cycles per chunk), and adding V in the reduce phase
-        // instead costs ~9 address instructions per load (measured: no gain).  b_p2 is added once per
-        // output instead of once per pair: a channel's softmax weights sum to one.
-        constexpr int GROUP = EPI_GROUP;
-        auto issue_v = [&](int cc, int slot) {
-            const uint32_t gst = smem_base + OFF_G + slot * G_STAGE;
-#pragma unroll
-            for (int it = 0; it < 4; ++it)
-                cp_async16(gst + (g_rbase + it * 4 + g_sub) * G_PITCH + g_piece * 16,
-                           p.vtab + (int64_t)gj[it] * d + cc * 32 + g_piece * 4);
-        };
-        // every warp has consumed the last Ka/Qa stage (its G_EMPTY arrival precedes this barrier)
-        asm volatile("barrier.sync 1, 256;" ::: "memory");
-        issue_v(0, 0);
-        if (ND > 1) issue_v(1, 1);
-        cp_async_commit();
-        long long t_wait = 0, t_stage = 0, t_bar = 0, t_red = 0, t0 = 0;
-        for (int g0 = 0; g0 < ND; g0 += GROUP) {
-            const int gn = min(GROUP, ND - g0);
-            if (dbg) t0 = clock64();
-            cp_async_wait_all();
-            asm volatile("barrier.sync 2, 288;" ::: "memory");         // V slices landed; previous group's tiles are free
-            if (dbg) t_bar += clock64() - t0;
-#pragma unroll
-            for (int u = 0; u < GROUP; ++u) {
-                if (u >= gn) break;
-                const int cc = g0 + u;
-                const int g = NC + cc;
-                const int b = g % NBUF;
-                const uint32_t use = (uint32_t)(g / NBUF);
-                if (dbg) t0 = clock64();
-                mbar_wait(BAR(ACC1_FULL + b), use & 1u);
-                tc_fence_after();
-                if (dbg) { const long long t1 = clock64(); t_wait += t1 - t0; t0 = t1; }
-                uint32_t dl[16], lg[16];
-                tmem_ld16_nowait(taddr + ACC1_COL + b * 32 + half * 16, dl);
-                tmem_ld16_nowait(taddr + cc * 32 + half * 16, lg);
-                float4 vv[4];
-                {
-                    const uint8_t* vs = smem + OFF_G + u * G_STAGE + r * G_PITCH + half * 64;
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) vv[e] = *reinterpret_cast<const float4*>(vs + 16 * e);
-                }
-                tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(BAR(A2_FULL + b));      // acc1[b] drained
-                float* sl = tile_ptr(2 * u) + r * STG_LD + half * 16;
-                float* sv = tile_ptr(2 * u + 1) + r * STG_LD + half * 16;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    sl[4 * e + 0] = __uint_as_float(lg[4 * e + 0]) * p.scale_log2;
-                    sl[4 * e + 1] = __uint_as_float(lg[4 * e + 1]) * p.scale_log2;
-                    sl[4 * e + 2] = __uint_as_float(lg[4 * e + 2]) * p.scale_log2;
-                    sl[4 * e + 3] = __uint_as_float(lg[4 * e + 3]) * p.scale_log2;
-                    sv[4 * e + 0] = __uint_as_float(dl[4 * e + 0]) + vv[e].x;
-                    sv[4 * e + 1] = __uint_as_float(dl[4 * e + 1]) + vv[e].y;
-                    sv[4 * e + 2] = __uint_as_float(dl[4 * e + 2]) + vv[e].z;
-                    sv[4 * e + 3] = __uint_as_float(dl[4 * e + 3]) + vv[e].w;
-                }
-                if (dbg) t_stage += clock64() - t0;
-            }
-            if (dbg) t0 = clock64();
-            asm volatile("barrier.sync 2, 288;" ::: "memory");         // the group's tiles are complete, V stages consumed
-            if (dbg) { const long long t1 = clock64(); t_bar += t1 - t0; t0 = t1; }
-            if (g0 + GROUP < ND) {                                  // next group's V slices: in flight during the reduce
-                issue_v(g0 + GROUP, 0);
-                if (g0 + GROUP + 1 < ND) issue_v(g0 + GROUP + 1, 1);
-                cp_async_commit();
-            }
-            if (dbg) { const long long t1 = clock64(); g_dbg[9] += t1 - t0; t0 = t1; }
-            // task = (chunk u, query q), dealt round-robin to the 8 row warps and the weight-stream warp
-            const int ntask = gn * p.tq;
-            for (int task = warp; task < ntask; task += EPI_WARPS) {
-                const int u = task >= p.tq ? 1 : 0, q = task - u * p.tq;
-                const int64_t gi = q0 + q;
-                if (gi < p.n)
-                    reduce_task<KT>(tile_ptr(2 * u), tile_ptr(2 * u + 1), q, k, lane, p.out + gi * d + (g0 + u) * 32,
-                                    p.bp2 + (g0 + u) * 32);
-            }
-            if (dbg) t_red += clock64() - t0;
-        }
-        if (dbg) { g_dbg[5] = t_wait; g_dbg[6] = t_stage; g_dbg[7] = t_bar; g_dbg[8] = t_red; }
-        if (dbg) g_dbg[3] = clock64();
-        tc_fence_before();
+        if (dbg) { g_dbg[1] = clock64(); g_dbg[10] = s_top; g_dbg[11] = s_acc1; g_dbg[12] = s_ld; g_dbg[13] = s_cvt; g_dbg[14] = s_st; }
     } else if (warp == ROW_WARPS) {
         // ================================================================== weight stream
         if (lane == 0) {
@@ -524,10 +471,9 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fused_kernel(const Params p) 
                 mbar_arrive_expect_tx(BAR(WC_FULL + s), 2 * WC_BYTES);
                 bulk_g2s(smem_base + OFF_WC + s * 2 * WC_BYTES, p.wmain + (size_t)c * wpacked, 2 * WC_BYTES, BAR(WC_FULL + s));
             };
-            load_wc(0);
-            if (NC > 1) load_wc(1);
+            for (int c = 0; c < WC_STAGES && c < NC; ++c) load_wc(c);
             for (int c = 0; c < NC; ++c) {
-                if (c + 2 < NC) load_wc(c + 2);              // the Wc ring runs ahead of the W_a2 ring
+                if (c + WC_STAGES < NC) load_wc(c + WC_STAGES);   // the Wc ring runs a full ring ahead (MMA1 leads MMA2 by NBUF chunks)
                 const int s = c & 1;
                 const uint32_t use = (uint32_t)(c >> 1);
                 mbar_wait(BAR(W_EMPTY + s), (use & 1u) ^ 1u);
@@ -543,33 +489,18 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fused_kernel(const Params p) 
             bulk_g2s(smem_base + OFF_W, p.wp2, (uint32_t)(2 * d * 64), BAR(W_FULL + 0));
         }
         __syncwarp();
-        // ---- epilogue helper: ninth reduce warp (same barrier sequence as the row warps' epilogue)
-        const int64_t q0 = (int64_t)blockIdx.x * p.tq;
-        for (int g0 = 0; g0 < ND; g0 += EPI_GROUP) {
-            const int gn = min(EPI_GROUP, ND - g0);
-            asm volatile("barrier.sync 2, 288;" ::: "memory");
-            asm volatile("barrier.sync 2, 288;" ::: "memory");         // the group's tiles are complete
-            const int ntask = gn * p.tq;
-            for (int task = ROW_WARPS; task < ntask; task += EPI_WARPS) {
-                const int u = task >= p.tq ? 1 : 0, q = task - u * p.tq;
-                const int64_t gi = q0 + q;
-                if (gi < p.n)
-                    reduce_task<KT>(tile_ptr(2 * u), tile_ptr(2 * u + 1), q, k, lane, p.out + gi * d + (g0 + u) * 32,
-                                    p.bp2 + (g0 + u) * 32);
-            }
-        }
-    } else {
+    } else if (warp == ROW_WARPS + 1) {
         // ================================================================== MMA issuers
         // Two issuing threads.  With a single one the loop was bound by that thread: per chunk
         // ~1080 cycles inside the MMA2 issue + commits (back-pressured by the tensor pipe), ~420 in the
         // MMA1 issue + commits, ~460 in three mbarrier waits, all serial (in-kernel stamps: 51.7 k of the
-        // 48.7 k loop).  Warp 9 issues MMA2 only; warp 10 issues MMA1 (and the delta contractions of the
+        // 48.7 k loop).  Warp 17 issues MMA2 only; warp 18 issues MMA1 (and the delta contractions of the
         // epilogue) and runs ahead.  Cross-thread ordering is explicit: MMA1(c) overwrites acc1[c % 3],
-        // which MMA2(c - 3) read as its A operand, so warp 10 waits on A2_EMPTY (committed by warp 9).
+        // which MMA2(c - 3) read as its A operand, so warp 18 waits on A2_EMPTY (committed by warp 17).
         // Shared-memory descriptors are loop invariant per (buffer, k-step, hi/lo, n-tile); the
         // addresses differ only in the 14-bit start field, so every descriptor is a constant
         // base plus a small per-buffer offset.
-        if (lane == 0 && warp == ROW_WARPS + 1) {
+        if (lane == 0) {
             const uint32_t idescN = umma_idesc(dn);
             const uint32_t lbo_b = (uint32_t)d * 16;
             const int split = p.split;
@@ -602,10 +533,15 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fused_kernel(const Params p) 
                 tc_fence_after();
                 mma2(c);
                 umma_commit(BAR(W_EMPTY + (c & 1)));
-                umma_commit(BAR(A2_EMPTY + c % NBUF));          // acc1[c % 3] may be overwritten by MMA1(c + 3)
+                umma_commit(BAR(A2_EMPTY + c % NBUF));          // completion: acc1[c % 3] has been read (delta phase, issue_mode 0)
+                tc_fence_before();                              // order the queued MMAs before the cross-thread signal
+                mbar_arrive(BAR(A2_ISSUED + c % NBUF));         // issue: MMA2(c) is in the tensor pipe's queue (see the MMA1 warp)
             }
             umma_commit(BAR(ACC2_FULL));
-        } else if (lane == 0 && warp == ROW_WARPS + 2) {
+        }
+        __syncwarp();
+    } else {
+        if (lane == 0) {
             const uint32_t idesc32 = umma_idesc(32);
             const uint32_t lbo_a = BM * 16, lbo_b = (uint32_t)d * 16;
             const int split = p.split;
@@ -633,9 +569,18 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fused_kernel(const Params p) 
             };
             mbar_wait(BAR(R_READY), 0);
             tc_fence_after();
+            // MMA1(c) overwrites acc1[c % 3], which MMA2(c - 3) reads as its A operand.  The tensor pipe executes in issue
+            // order, so MMA1(c) only has to be ISSUED after MMA2(c - 3) -- it need not wait for its completion
+            // (issue_mode 1, default: the MMA2 thread arrives on A2_ISSUED right after queueing MMA2(c - 3)).  Waiting
+            // for the completion instead (issue_mode 0, A2_EMPTY) queued MMA1(c) BEHIND MMA2(c - 2), so the conversion
+            // of chunk c could start only one MMA2 later and the loop period became MMA1 + the conversion latency
+            // (~1.3 k cycles per chunk for ANY number of MMA2 passes: 38.8 k / 34.1 k / 32.7 k cycles per tile with
+            // 3 / 2 / 1 passes, in-kernel stamps) instead of the MMA2 time.  (One thread issuing both in program order is
+            // correct as well but serialises the issue and the waits: 44.5 k.)
+            const bool by_issue = p.issue_mode == 1;
             for (int c = 0; c < NC; ++c) {
                 mbar_wait(BAR(WC_FULL + c % WC_STAGES), (uint32_t)(c / WC_STAGES) & 1u);
-                if (c >= NBUF) mbar_wait(BAR(A2_EMPTY + c % NBUF), (uint32_t)(c / NBUF - 1) & 1u);   // MMA2(c - 3) retired
+                if (c >= NBUF) mbar_wait(BAR((by_issue ? A2_ISSUED : A2_EMPTY) + c % NBUF), (uint32_t)(c / NBUF - 1) & 1u);
                 tc_fence_after();
                 mma1(c);
                 umma_commit(BAR(ACC1_FULL + c % NBUF));
@@ -678,6 +623,112 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fused_kernel(const Params p) 
                 umma_commit(BAR(ACC1_FULL + b));
             }
         }
+    }
+
+    if (warp <= ROW_WARPS + 1) {
+        // ================================================================== softmax / aggregation epilogue
+        // 16 row warps stage, 18 warps (+ weight-stream warp, + MMA2 warp: both idle by now) reduce.  All 18 run THIS
+        // code, so every warp reaches the named barrier through the same (aligned) instruction.
+        // Staging tiles [row][33] of one 32-channel chunk (padding: conflict-free row-wise stores and column-wise
+        // loads): logits * scale and V + delta, 16.5 KB each.  The per-channel softmax over a query's k rows is a
+        // reduction ACROSS TMEM lanes, so it goes through shared memory.  Chunks are processed in groups of two
+        // (4 tiles: 3 over the idle hidden-buffer region / Wc ring, 1 over the idle W stage 1; W_p2 sits in W stage 0);
+        // conversion group g stages chunk u = g of a group (its 256 threads cover the 128 x 32 block), and the
+        // 2 x tq (chunk, query) tasks are dealt round-robin to the 18 warps: ONE round at k = 14.
+        // The V_j slices of a group are fetched one group ahead into the two group-0 gather stages by the same
+        // cooperative cp.async pattern as Ka in the main loop: a row-per-thread gather from global costs one L1
+        // wavefront per lane (~1000 LSU cycles per chunk), and adding V in the reduce phase instead costs ~9 address
+        // instructions per load (measured: no gain).  b_p2 is added once per output instead of once per pair: a
+        // channel's softmax weights sum to one.
+        constexpr int GROUP = EPI_GROUP;
+        static_assert(GROUP == ROW_GROUPS, "one chunk of a group per conversion group");
+        auto issue_v = [&](int cc, int slot) {
+            const uint32_t gst = smem_base + OFF_G + slot * G_STAGE;
+#pragma unroll
+            for (int it = 0; it < 4; ++it)
+                cp_async16(gst + (g_rbase + it * 4 + g_sub) * G_PITCH + g_piece * 16,
+                           p.vtab + (int64_t)gj[it] * d + cc * 32 + g_piece * 4);
+        };
+        long long t_wait = 0, t_stage = 0, t_bar = 0, t_red = 0, t0 = 0;
+        if (is_row) {
+            mbar_wait(BAR(ACC2_FULL), 0);
+            tc_fence_after();
+            if (dbg) g_dbg[2] = clock64();
+            // every warp of both groups has consumed its last Ka/Qa stage (its G_EMPTY arrival precedes this barrier):
+            // from here on the group-0 stages hold V slices and the hidden-buffer region (group 1's stages) holds tiles
+            __syncwarp();
+            asm volatile("bar.sync 1, %0;" ::"n"(ROW_THREADS) : "memory");
+            if (grp < ND) issue_v(grp, grp);
+            cp_async_commit();
+        }
+        for (int g0 = 0; g0 < ND; g0 += GROUP) {
+            const int gn = min(GROUP, ND - g0);
+            if (dbg) t0 = clock64();
+            if (is_row) cp_async_wait_all();
+            __syncwarp();
+            asm volatile("bar.sync 2, %0;" ::"n"(EPI_THREADS) : "memory");      // V slices landed; previous group's tiles are free
+            if (dbg) t_bar += clock64() - t0;
+            if (is_row && grp < gn) {
+                const int u = grp;
+                const int cc = g0 + u;
+                const int g = NC + cc;
+                const int b = g % NBUF;
+                const uint32_t use = (uint32_t)(g / NBUF);
+                if (dbg) t0 = clock64();
+                mbar_wait(BAR(ACC1_FULL + b), use & 1u);
+                tc_fence_after();
+                if (dbg) { const long long t1 = clock64(); t_wait += t1 - t0; t0 = t1; }
+                uint32_t dl[16], lg[16];
+                tmem_ld16_nowait(taddr + ACC1_COL + b * 32 + half * 16, dl);
+                tmem_ld16_nowait(taddr + cc * 32 + half * 16, lg);
+                float4 vv[4];
+                {
+                    const uint8_t* vs = smem + OFF_G + u * G_STAGE + r * G_PITCH + half * 64;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) vv[e] = *reinterpret_cast<const float4*>(vs + 16 * e);
+                }
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(A2_FULL + b));      // acc1[b] drained
+                float* sl = tile_ptr(2 * u) + r * STG_LD + half * 16;
+                float* sv = tile_ptr(2 * u + 1) + r * STG_LD + half * 16;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    sl[4 * e + 0] = __uint_as_float(lg[4 * e + 0]) * p.scale_log2;
+                    sl[4 * e + 1] = __uint_as_float(lg[4 * e + 1]) * p.scale_log2;
+                    sl[4 * e + 2] = __uint_as_float(lg[4 * e + 2]) * p.scale_log2;
+                    sl[4 * e + 3] = __uint_as_float(lg[4 * e + 3]) * p.scale_log2;
+                    sv[4 * e + 0] = __uint_as_float(dl[4 * e + 0]) + vv[e].x;
+                    sv[4 * e + 1] = __uint_as_float(dl[4 * e + 1]) + vv[e].y;
+                    sv[4 * e + 2] = __uint_as_float(dl[4 * e + 2]) + vv[e].z;
+                    sv[4 * e + 3] = __uint_as_float(dl[4 * e + 3]) + vv[e].w;
+                }
+                if (dbg) t_stage += clock64() - t0;
+            }
+            if (dbg) t0 = clock64();
+            __syncwarp();
+            asm volatile("bar.sync 2, %0;" ::"n"(EPI_THREADS) : "memory");      // the group's tiles are complete, V stages consumed
+            if (dbg) { const long long t1 = clock64(); t_bar += t1 - t0; t0 = t1; }
+            if (is_row) {                                                       // next group's V slices: in flight during the reduce
+                if (g0 + GROUP + grp < ND) issue_v(g0 + GROUP + grp, grp);
+                cp_async_commit();
+            }
+            if (dbg) { const long long t1 = clock64(); g_dbg[9] += t1 - t0; t0 = t1; }
+            // task = (chunk u, query q)
+            const int ntask = gn * p.tq;
+            for (int task = warp; task < ntask; task += EPI_WARPS) {
+                const int u = task >= p.tq ? 1 : 0, q = task - u * p.tq;
+                const int64_t gi = q0 + q;
+                if (gi < p.n)
+                    reduce_task<KT>(tile_ptr(2 * u), tile_ptr(2 * u + 1), q, k, lane, p.out + gi * d + (g0 + u) * 32,
+                                    p.bp2 + (g0 + u) * 32);
+            }
+            if (dbg) t_red += clock64() - t0;
+        }
+        if (dbg) { g_dbg[5] = t_wait; g_dbg[6] = t_stage; g_dbg[7] = t_bar; g_dbg[8] = t_red; }
+        if (dbg) g_dbg[3] = clock64();
+        if (is_row) tc_fence_before();
     }
 #undef BAR
     __syncthreads();
@@ -791,6 +842,14 @@ int attn_fused_launch(const PtBlockParams& P, const AttnTables& T, const float* 
         int mode = g_fused_mma2_mode.load(std::memory_order_relaxed);
         if (mode == 0) mode = fused_mode_default();
         p.split = (precision == 1) ? mode : 0;
+    }
+    {
+        static int im = -1;
+        if (im < 0) {
+            const char* e = getenv("O4D_FUSED_ISSUE");          // 0 = MMA1 waits for MMA2's completion (A/B timing)
+            im = (e && e[0] == '0') ? 0 : 1;
+        }
+        p.issue_mode = im;
     }
     p.scale_log2 = (float)(1.4426950408889634 / sqrt((double)d));
     const int64_t tiles = cdiv(n, p.tq);

@@ -359,7 +359,7 @@ static int decoder_forward_chain(const o4d_decoder_config* c, const DecParams& d
                                  float* out, float* penult, cudaStream_t st) {
     const int H = c->d_hidden, E = c->d_latent_local;
     O4D_TRY(act_image_launch(in_ptr, in_w, nq, in_w, 0, w.img_pe, st));
-    O4D_TRY(act_image_launch(w.f_loc, E, nq, E, 0, w.img_floc, st));
+    // w.img_floc: written by the local-feature blend itself (decoder_forward)
     float* qa = (float*)w.sub;                        // (nq, 2H): first carve of the attention workspace
     ChainBuild cb(nq, c->precision == 1 ? 1 : 0, st);
     // implicit.py:403-408 + :416-418 of block 0:  x = lin_in(pe) + lin_z[0](f_query)
@@ -434,7 +434,10 @@ int decoder_forward(const o4d_decoder_config* c, const float* const* P, const vo
 
     // implicit.py:328-339  K_l nearest abstract points, inverse-distance blend of their features
     O4D_TRY(knn_launch(query, nq, c->d_in, s.abs_xyz, m, 3, c->num_local_features, 1, w.idx_l, nullptr, w.dist_l, st));
-    O4D_TRY(local_blend_launch(w.idx_l, w.dist_l, s.abs_feat, E, nq, c->num_local_features, E, w.f_loc, E, st));
+    // (fused multi-layer path: straight into the activation image lin_z's layers read; no fp32 copy is needed)
+    const bool chain = w.img_x != nullptr && nq >= 1024;
+    O4D_TRY(local_blend_launch(w.idx_l, w.dist_l, s.abs_feat, E, nq, c->num_local_features, E, w.f_loc, E, st,
+                               chain ? w.img_floc : nullptr));
     // point_transformer_layer.py:167 -- identical for every cross layer (same query / abstract cloud)
     if (c->cross_attn_layers > 0)
         O4D_TRY(knn_launch(query, nq, c->d_in, s.abs_xyz, m, 3, c->cross_attn_neighbors, 0, w.idx_c, nullptr, nullptr, st));
@@ -449,7 +452,7 @@ int decoder_forward(const o4d_decoder_config* c, const float* const* P, const vo
     const float* in_ptr = c->pos_encoding_freqs > 0 ? w.pe : query;
     const int in_w = c->pos_encoding_freqs > 0 ? pe_w : c->d_in;
     if (c->pos_encoding_freqs > 0) O4D_TRY(posenc_launch(query, nq, c->d_in, c->pos_encoding_freqs, w.pe, st));
-    if (w.img_x && nq >= 1024) {
+    if (chain) {
         if (!fold) {
             set_error("decoder: fused MLP path selected but the folded weights are missing");
             return O4D_E_ARG;

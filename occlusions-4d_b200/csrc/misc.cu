@@ -1,6 +1,7 @@
 // Small bandwidth-bound kernels of the path: Fourier encoding, inverse-distance feature
 // blend, neighbourhood max-pool, LayerNorm+ReLU, row gathers, column mean.
 #include "o4d_common.cuh"
+#include <cuda_bf16.h>
 #include <math.h>
 
 namespace o4d {
@@ -43,10 +44,13 @@ int posenc_launch(const float* q, int64_t n, int d_in, int n_freq, float* out, c
 
 // model/implicit.py:337-339: w = 1/(dist+1e-4); w /= sum|w| (F.normalize p=1, eps 1e-12);
 // out_i = sum_k w_k feat[idx_k].  One warp per query, lanes stride over channels.
+// IMG: write the bf16 hi / lo activation image of the fused multi-layer kernel (mlp_chain.cuh layout, ceil(e / 32)
+// chunks per 128-row tile, padding columns zero) instead of fp32 rows -- lin_z's operand, read by six layers.
+template <bool IMG>
 __global__ void __launch_bounds__(256)
 local_blend_kernel(const int32_t* __restrict__ idx, const float* __restrict__ dist,
                    const float* __restrict__ feat, int64_t ldfeat, int64_t n, int k, int e,
-                   float* __restrict__ out, int64_t ldout) {
+                   float* __restrict__ out, int64_t ldout, uint8_t* __restrict__ img) {
     const int lane = threadIdx.x & 31;
     const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= n) return;
@@ -62,21 +66,40 @@ local_blend_kernel(const int32_t* __restrict__ idx, const float* __restrict__ di
         }
     }
     const float denom = fmaxf(sum, 1e-12f);
-    for (int c = lane; c < e; c += 32) {
+    const int cpt = (e + 31) / 32;
+    for (int c = lane; c < (IMG ? cpt * 32 : e); c += 32) {
         float acc = 0.f;
+        if (c < e) {
 #pragma unroll
-        for (int j = 0; j < O4D_MAX_K; ++j) {
-            if (j < k) acc = fmaf(w[j] / denom, feat[(int64_t)id[j] * ldfeat + c], acc);
+            for (int j = 0; j < O4D_MAX_K; ++j) {
+                if (j < k) acc = fmaf(w[j] / denom, feat[(int64_t)id[j] * ldfeat + c], acc);
+            }
         }
-        out[i * ldout + c] = acc;
+        if (!IMG) {
+            out[i * ldout + c] = acc;
+        } else {
+            const __nv_bfloat16 hi = __float2bfloat16_rn(acc);
+            const __nv_bfloat16 lo = __float2bfloat16_rn(acc - __bfloat162float(hi));
+            const uint32_t h = __bfloat16_as_ushort(hi), l = __bfloat16_as_ushort(lo);
+            const uint32_t h1 = __shfl_down_sync(0xffffffffu, h, 1), l1 = __shfl_down_sync(0xffffffffu, l, 1);
+            if ((lane & 1) == 0) {
+                uint8_t* dst = img + ((size_t)(i >> 7) * cpt + (c >> 5)) * 16384 + (lane >> 3) * 2048 + (((int)i & 127) >> 3) * 128 +
+                               ((int)i & 7) * 16 + (lane & 7) * 2;
+                *reinterpret_cast<uint32_t*>(dst) = h | (h1 << 16);
+                *reinterpret_cast<uint32_t*>(dst + 8192) = l | (l1 << 16);
+            }
+        }
     }
 }
 
 int local_blend_launch(const int32_t* idx, const float* dist, const float* feat, int64_t ldfeat,
-                       int64_t n, int k, int e, float* out, int64_t ldout, cudaStream_t st) {
+                       int64_t n, int k, int e, float* out, int64_t ldout, cudaStream_t st, void* img) {
     if (n == 0) return 0;
     O4D_REQUIRE(k >= 1 && k <= O4D_MAX_K, "local blend: k=%d outside [1,%d]", k, O4D_MAX_K);
-    local_blend_kernel<<<(unsigned)cdiv(n, 8), 256, 0, st>>>(idx, dist, feat, ldfeat, n, k, e, out, ldout);
+    if (img)
+        local_blend_kernel<true><<<(unsigned)cdiv(n, 8), 256, 0, st>>>(idx, dist, feat, ldfeat, n, k, e, out, ldout, (uint8_t*)img);
+    else
+        local_blend_kernel<false><<<(unsigned)cdiv(n, 8), 256, 0, st>>>(idx, dist, feat, ldfeat, n, k, e, out, ldout, nullptr);
     O4D_LAUNCH_CHECK();
     return 0;
 }

@@ -33,12 +33,12 @@ using namespace tch;
 
 constexpr int BK = 32;
 constexpr int STAGES = 4;
-constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARPS = 16;                            // four warps per TMEM lane quarter (column quarters)
 constexpr int THREADS = (EPI_WARPS + 2) * 32;
 constexpr int A_HALF = BM * BK * 2;                      // 8 KB: one bf16 image half of a chunk
 constexpr int W_BYTES_MAX = 2 * BN_MAX * BK * 2;         // hi + lo slab of a 208-column n-tile
 constexpr int STAGE_BYTES = IMG_CHUNK_BYTES + W_BYTES_MAX;
-constexpr int SLD = 36;                                  // epilogue staging row pitch (floats)
+constexpr int SLD = 20;                                  // epilogue staging row pitch (floats): 32 rows x 16 columns per warp
 constexpr int STG_BYTES = EPI_WARPS * 32 * SLD * 4;
 constexpr int OFF_STG = STAGES * STAGE_BYTES;
 constexpr int OFF_BAR = OFF_STG + STG_BYTES;
@@ -66,6 +66,13 @@ __device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
     return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
 
+// Cycle counters of one CTA (O4D_STAMPS builds only, o4d_debug_read_chain): which wait bounds the pipeline.
+// [0] MMA thread total, [1] its wait for a free accumulator (epilogue-bound), [2] its wait for a full stage (load-bound),
+// [3] producer total wait for an empty stage (MMA-bound), [4] producer wait for the tile's previous layer (dependency),
+// [5] epilogue warp 0 wait for a full accumulator, [6] epilogue warp 0 busy
+__device__ long long g_dbg_chain[8];
+#define CHAIN_T0() (O4D_STAMPS ? clock64() : 0LL)
+
 // PAIR = true: two CTAs of a cluster (one TPC) work as a pair (tcgen05 cta_group::2).  Each owns one 128-row tile of a
 // tile pair and its own A-image stream, but loads only HALF of every weight slab; the leader's MMA thread issues
 // M = 256 instructions that read B half from each CTA's shared memory.  Weight bytes per SM halve: 42.6 -> 29.3 KB
@@ -82,6 +89,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const Program P) 
     // full[4], empty[4], acc_full[2], acc_empty[2]; then the TMEM slot and the per-warp progress counters
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
     int* done = reinterpret_cast<int*>(bars + 13);       // [EPI_WARPS] items finished by each epilogue warp
+    static_assert(13 * 8 + EPI_WARPS * 4 <= 256, "barrier area");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]);
     const uint32_t accf0 = smem_u32(&bars[2 * STAGES]), acce0 = smem_u32(&bars[2 * STAGES + 2]);
@@ -130,17 +138,24 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const Program P) 
 
     if (warp < EPI_WARPS) {
         // ================================================================== epilogue warps
-        const int quarter = warp & 3, chalf = warp >> 2;
+        // Sixteen warps: TMEM lane quarter warp & 3, column part warp >> 2 (a quarter of the n-tile's 16-column blocks).
+        // (Measured with in-kernel counters, eight warps and 32-column blocks: the epilogue warps were busy 90 % of the
+        // kernel and the MMA thread spent 40 % of its time waiting for a drained accumulator -- 18.7 k cycles of epilogue
+        // per 128 x 208 item against 8.1 - 13.7 k of MMA -- at an IPC of ~0.2: dependent tcgen05.ld -> STS -> LDS -> FADD ->
+        // STG chains with two warps per scheduler.  Four warps per scheduler hide that latency.)
+        const int quarter = warp & 3, cpart = warp >> 2;
         const uint32_t taddr_q = tmem_base + ((uint32_t)(quarter * 32) << 16);
         float* stg = reinterpret_cast<float*>(smem + OFF_STG) + warp * (32 * SLD);
         int item = 0;
+        const bool dbg = O4D_STAMPS && blockIdx.x == gridDim.x / 2 && threadIdx.x == 0;
+        long long t_wait = 0, t_busy = 0;
         for (int o = 0; o < P.nops; ++o) {
             const Op& op = P.op[o];
             const int bn = op.bn;
             const bool relu_img = op.img_relu != 0;
-            const int nblk = (bn + 31) / 32;
-            const int c_begin = chalf ? ((nblk + 1) / 2) * 32 : 0;
-            const int c_end = chalf ? bn : min(bn, ((nblk + 1) / 2) * 32);
+            const int nblk = bn / 16;                                   // bn is a multiple of 16
+            const int c_begin = ((nblk * cpart) / 4) * 16;
+            const int c_end = ((nblk * (cpart + 1)) / 4) * 16;
             const bool image_only = op.out == nullptr && op.res == nullptr;
             const bool vec_ok = (op.n % 4 == 0) && (!op.out || ((op.ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(op.out) & 15) == 0))) &&
                                 (!op.res || ((op.ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(op.res) & 15) == 0))) &&
@@ -151,15 +166,33 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const Program P) 
                 const int rows_here = (int)max((int64_t)0, min((int64_t)32, P.rows - row0));
                 for (int nh = 0; nh < op.ntiles; ++nh, ++item) {
                     const int acc = item & 1;
+                    const int col_base = nh * bn;
+                    // residual rows of the first 16-column block: requested BEFORE the wait for the accumulator (they do
+                    // not depend on it), so their L2 latency hides behind the item's MMAs
+                    const int rr = lane >> 2, c4 = (lane & 3) * 4;
+                    float4 resn[4];
+                    auto load_res = [&](int c0) {
+                        const int gc = col_base + c0 + c4;
+                        const bool ok = op.res != nullptr && gc < op.n && c0 < c_end;
+#pragma unroll
+                        for (int it = 0; it < 4; ++it) {
+                            const int row = it * 8 + rr;
+                            resn[it] = (ok && row < rows_here) ? *reinterpret_cast<const float4*>(op.res + (row0 + row) * op.ldr + gc)
+                                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    };
+                    if (!image_only && vec_ok) load_res(c_begin);
+                    const long long te0 = CHAIN_T0();
                     if (PAIR) mbar_wait_cl(accf0 + 8 * acc, (uint32_t)(item >> 1) & 1u);
                     else mbar_wait(accf0 + 8 * acc, (uint32_t)(item >> 1) & 1u);
                     tc_fence_after();
+                    const long long te1 = CHAIN_T0();
                     const uint32_t taddr = taddr_q + (uint32_t)(acc * 256);
-                    const int col_base = nh * bn;
                     if (image_only) {
                         // ---- (E1) row per thread: + bias, ReLU, split, two 16-byte lines per 8 columns.  A warp
                         // instruction stores 32 rows x 16 B = 512 contiguous bytes of the image.
                         const int trow = quarter * 32 + lane;
+                        uint8_t* img_row = op.img + (size_t)tile * op.img_cpt * IMG_CHUNK_BYTES + (trow >> 3) * 128 + (trow & 7) * 16;
                         for (int c0 = c_begin; c0 < c_end; c0 += 16) {
                             float v[16];
                             tmem_ld16(taddr + (uint32_t)c0, v);
@@ -189,47 +222,37 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const Program P) 
                                     hi[e] = pack2(h0, h1);
                                     lo[e] = pack2(l0, l1);
                                 }
-                                uint8_t* dst = op.img + img_off(tile, op.img_cpt, trow, gc);
+                                uint8_t* dst = img_row + (size_t)(gc >> 5) * IMG_CHUNK_BYTES + ((gc & 31) >> 3) * (BM * 16);
                                 *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                                 *reinterpret_cast<uint4*>(dst + A_HALF) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                             }
                         }
                     } else if (vec_ok) {
-                        // ---- (E2) fp32 output and / or residual: 32 x 32 blocks transposed through a padded staging
-                        // tile so that residual loads and output stores are contiguous 128-byte row segments; the
-                        // image (if any) is written from the same mapping: 4 columns = half a core-matrix line.
-                        const int rr = lane >> 3, c4 = (lane & 7) * 4;
-                        float4 resn[8];
-                        auto load_res = [&](int c0) {
+                        // ---- (E2) fp32 output and / or residual: 32 x 16 blocks transposed through a padded staging tile:
+                        // in the write phase a lane owns (row rr of an 8-row group, 4 columns), so residual loads and
+                        // output stores are 64 contiguous bytes per row (whole sectors), and the image (if any) is
+                        // written from the same mapping: 4 columns = half a core-matrix line, 8 consecutive rows = 128 B.
+                        uint8_t* img_rows = op.img ? op.img + (size_t)tile * op.img_cpt * IMG_CHUNK_BYTES + (quarter * 4) * 128 + rr * 16
+                                                   : nullptr;      // + it * 128: row quarter*32 + it*8 + rr
+                        for (int c0 = c_begin; c0 < c_end; c0 += 16) {
                             const int gc = col_base + c0 + c4;
-                            const bool ok = op.res && c4 < min(32, bn - c0) && gc < op.n;
+                            const bool col_ok = gc < op.n;
+                            float4 res[4];
 #pragma unroll
-                            for (int it = 0; it < 8; ++it) {
-                                const int row = it * 4 + rr;
-                                resn[it] = (ok && row < rows_here) ? *reinterpret_cast<const float4*>(op.res + (row0 + row) * op.ldr + gc)
-                                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
-                            }
-                        };
-                        if (c_begin < c_end) load_res(c_begin);
-                        for (int c0 = c_begin; c0 < c_end; c0 += 32) {
-                            const int width = min(32, bn - c0);
-                            float4 res[8];
-#pragma unroll
-                            for (int it = 0; it < 8; ++it) res[it] = resn[it];
-                            if (c0 + 32 < c_end) load_res(c0 + 32);
-                            float v[32];
+                            for (int it = 0; it < 4; ++it) res[it] = resn[it];
+                            load_res(c0 + 16);                          // next block's residual rows: in flight during this block
+                            float v[16];
                             tmem_ld16(taddr + (uint32_t)c0, v);
-                            if (width > 16) tmem_ld16(taddr + (uint32_t)(c0 + 16), v + 16);
 #pragma unroll
-                            for (int i = 0; i < 32; i += 4)
-                                if (i < width) *reinterpret_cast<float4*>(stg + lane * SLD + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                            for (int i = 0; i < 16; i += 4)
+                                *reinterpret_cast<float4*>(stg + lane * SLD + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
                             __syncwarp();
-                            const int gc = col_base + c0 + c4;
-                            if (c4 < width && gc < op.n) {
+                            if (col_ok) {
                                 const float4 bv = op.bias ? *reinterpret_cast<const float4*>(op.bias + gc) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                const size_t img_col = (size_t)(gc >> 5) * IMG_CHUNK_BYTES + ((gc & 31) >> 3) * (BM * 16) + (gc & 7) * 2;
 #pragma unroll
-                                for (int it = 0; it < 8; ++it) {
-                                    const int row = it * 4 + rr;
+                                for (int it = 0; it < 4; ++it) {
+                                    const int row = it * 8 + rr;
                                     float4 x = *reinterpret_cast<const float4*>(stg + row * SLD + c4);
                                     x.x += bv.x + res[it].x; x.y += bv.y + res[it].y; x.z += bv.z + res[it].z; x.w += bv.w + res[it].w;
                                     if (op.out && row < rows_here) *reinterpret_cast<float4*>(op.out + (row0 + row) * op.ldo + gc) = x;
@@ -238,7 +261,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const Program P) 
                                         __nv_bfloat16 h0, l0, h1, l1, h2, l2, h3, l3;
                                         split_bf16(x.x, h0, l0); split_bf16(x.y, h1, l1);
                                         split_bf16(x.z, h2, l2); split_bf16(x.w, h3, l3);
-                                        uint8_t* dst = op.img + img_off(tile, op.img_cpt, quarter * 32 + row, gc);
+                                        uint8_t* dst = img_rows + it * 128 + img_col;
                                         *reinterpret_cast<uint2*>(dst) = make_uint2(pack2(h0, h1), pack2(h2, h3));
                                         *reinterpret_cast<uint2*>(dst + A_HALF) = make_uint2(pack2(l0, l1), pack2(l2, l3));
                                     }
@@ -275,14 +298,18 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const Program P) 
                     fence_proxy_async_all();
                     __syncwarp();
                     if (lane == 0) st_release_shared(done0 + 4 * warp, item + 1);
+                    if (dbg) { t_wait += te1 - te0; t_busy += clock64() - te1; }
                 }
             }
         }
+        if (dbg) { g_dbg_chain[5] = t_wait; g_dbg_chain[6] = t_busy; }
     } else if (warp == EPI_WARPS) {
         // ================================================================== producer: A-image chunks + weight slabs
         if (lane == 0) {
             int g = 0;            // running stage counter
             int items_before = 0; // items of all earlier ops
+            const bool dbg = O4D_STAMPS && blockIdx.x == gridDim.x / 2;
+            long long t_empty = 0, t_dep = 0;
             int prev_nt = 0;      // n-tiles per row tile of the previous op
             for (int o = 0; o < P.nops; ++o) {
                 const Op& op = P.op[o];
@@ -291,6 +318,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const Program P) 
                 const int nch = op.k1c + op.k2c;
                 for (int j = 0; j < ntl; ++j) {
                     const int64_t tile = tile_of(j);
+                    const long long td0 = CHAIN_T0();
                     if (o > 0) {
                         // the images this op reads were written by the previous op's epilogues of THIS tile: wait
                         // until every epilogue warp has finished its last item of (o - 1, j)
@@ -305,6 +333,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const Program P) 
                         }
                         fence_proxy_async_all();
                     }
+                    if (dbg) t_dep += clock64() - td0;
                     const uint8_t* a1 = op.a1 + (size_t)tile * op.k1c * IMG_CHUNK_BYTES;
                     const uint8_t* a2 = op.a2 ? op.a2 + (size_t)tile * op.k2c * IMG_CHUNK_BYTES : nullptr;
                     for (int nh = 0; nh < op.ntiles; ++nh) {
@@ -314,8 +343,10 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const Program P) 
                         for (int c = 0; c < nch; ++c, ++g) {
                             const int s = g % STAGES;
                             const uint32_t ph = (uint32_t)(g / STAGES) & 1u;
+                            const long long tp0 = CHAIN_T0();
                             if (PAIR) mbar_wait_cl(empty0 + 8 * s, ph ^ 1u);
                             else mbar_wait(empty0 + 8 * s, ph ^ 1u);
+                            if (dbg) t_empty += clock64() - tp0;
                             const uint32_t dst = smem_base + s * STAGE_BYTES;
                             mbar_arrive_expect_tx(full0 + 8 * s, IMG_CHUNK_BYTES + w_bytes);
                             const uint8_t* asrc = c < op.k1c ? a1 + (size_t)c * IMG_CHUNK_BYTES : a2 + (size_t)(c - op.k1c) * IMG_CHUNK_BYTES;
@@ -327,12 +358,16 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const Program P) 
                 items_before += ntl * op.ntiles;
                 prev_nt = op.ntiles;
             }
+            if (dbg) { g_dbg_chain[3] = t_empty; g_dbg_chain[4] = t_dep; }
         }
     } else {
         // ================================================================== MMA issuer (pair: the leader's; the peer's warp forwards)
         if (lane == 0 && rank == 0) {
             int g = 0, item = 0;
             const uint32_t lbo_a = BM * 16;
+            const bool dbg = O4D_STAMPS && blockIdx.x == gridDim.x / 2;
+            const long long tm_start = CHAIN_T0();
+            long long t_acc = 0, t_full = 0;
             for (int o = 0; o < P.nops; ++o) {
                 const Op& op = P.op[o];
                 const int bn = op.bn;
@@ -345,16 +380,20 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const Program P) 
                     for (int nh = 0; nh < op.ntiles; ++nh, ++item) {
                         const int acc = item & 1;
                         // accumulator free?  (its previous user was item - 2)
+                        const long long ta0 = CHAIN_T0();
                         if (PAIR) mbar_wait_cl(acce0 + 8 * acc, ((uint32_t)(item >> 1) & 1u) ^ 1u);
                         else mbar_wait(acce0 + 8 * acc, ((uint32_t)(item >> 1) & 1u) ^ 1u);
                         tc_fence_after();
+                        if (dbg) t_acc += clock64() - ta0;
                         const uint32_t dcol = tmem_base + (uint32_t)(acc * 256);
                         for (int c = 0; c < nch; ++c, ++g) {
                             const int s = g % STAGES;
                             const uint32_t ph = (uint32_t)(g / STAGES) & 1u;
+                            const long long tf0 = CHAIN_T0();
                             if (PAIR) mbar_wait_cl(full0 + 8 * s, ph);
                             else mbar_wait(full0 + 8 * s, ph);
                             tc_fence_after();
+                            if (dbg) t_full += clock64() - tf0;
                             const uint32_t a_hi = smem_base + s * STAGE_BYTES;
                             const uint32_t a_lo = a_hi + A_HALF;
                             const uint32_t b_hi = a_hi + IMG_CHUNK_BYTES;
@@ -387,6 +426,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const Program P) 
                     }
                 }
             }
+            if (dbg) { g_dbg_chain[0] = clock64() - tm_start; g_dbg_chain[1] = t_acc; g_dbg_chain[2] = t_full; g_dbg_chain[7] = item; }
         } else if (PAIR && lane == 0) {
             // peer: tell the leader's MMA thread when THIS CTA's share of a stage (its A rows, its half of the weight
             // slab) has landed.  A stage cannot be refilled before the leader has consumed it, so no phase is skipped.
@@ -628,4 +668,8 @@ extern "C" int o4d_resblock_forward_f32(const float* x, int64_t rows, int d, int
     f1.n = d; f1.k_alg = d_hidden;
     mlp_chain_tiling(d, &f1.bn, &f1.ntiles);
     return mlp_chain_launch(prog, st);
+}
+
+extern "C" int o4d_debug_read_chain(long long* out8) {
+    return (int)cudaMemcpyFromSymbol(out8, o4d::mc::g_dbg_chain, sizeof(long long) * 8);
 }

@@ -230,8 +230,9 @@ int down_launch(const float* const* p, const float* x, int64_t n, int d_in, cons
 
 // misc elementwise / gather kernels (misc.cu)
 int posenc_launch(const float* q, int64_t n, int d_in, int n_freq, float* out, cudaStream_t st);
+// img != nullptr: the blend is written as an activation image (ceil(e / 32) chunks per 128-row tile) instead of fp32 rows
 int local_blend_launch(const int32_t* idx, const float* dist, const float* feat, int64_t ldfeat,
-                       int64_t n, int k, int e, float* out, int64_t ldout, cudaStream_t st);
+                       int64_t n, int k, int e, float* out, int64_t ldout, cudaStream_t st, void* img = nullptr);
 int gather_max_launch(const float* y, int64_t ldy, const int32_t* nbr, int64_t n_out, int k, int d,
                       float* z, cudaStream_t st);
 int layernorm_relu_launch(float* y, int64_t rows, int d, const float* gamma, const float* beta,

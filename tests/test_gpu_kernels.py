@@ -173,6 +173,19 @@ def test_fused_residual_block_matches_fp64(rows, d, dh):
                         b1.to(DEV)[:40].contiguous(), precision=1) is None      # width 40: not a whole image chunk
 
 
+def test_fused_residual_block_cta_pair_variant_in_a_subprocess():
+    """O4D_CHAIN_PAIR=1 selects the cta_group::2 instantiation of the fused multi-layer kernel (different packed-weight
+    format, cluster launch); the switch is read once per process, so the same parity test runs in a child process."""
+    import subprocess
+    import sys
+    env = dict(os.environ, O4D_CHAIN_PAIR='1')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, '-m', 'pytest', os.path.join(root, 'tests', 'test_gpu_kernels.py'), '-q', '-m', 'gpu',
+                          '-k', 'fused_residual_block_matches_fp64 and (3001 or 1500)', '-p', 'no:cacheprovider'],
+                         env=env, cwd=root, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and '2 passed' in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
 def test_linear_strided_views_and_inplace_residual():
     g = torch.Generator().manual_seed(9)
     base = torch.randn(500, 291, generator=g)

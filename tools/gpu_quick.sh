@@ -29,3 +29,6 @@ if [ "$SKIP_SAN" != "1" ]; then
 timeout 300 compute-sanitizer --tool synccheck --error-exitcode 9 --print-limit 5 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_models.py -m gpu -x -q -k "fused_residual_block and 1024 or fused_attention_decoder_shapes" > $OUT/synccheck.log 2>&1; echo "synccheck exit $?"
 grep -E "ERROR SUMMARY|passed|failed|at void" $OUT/synccheck.log | sort | uniq -c | tail -8
 fi
+if [ -f occlusions-4d_b200/o4d/libo4d_stamps.so ] && [ "$SKIP_STAMPS" != "1" ]; then
+O4D_LIB=$PWD/occlusions-4d_b200/o4d/libo4d_stamps.so timeout 300 python tools/stamps_fused.py > $OUT/stamps.log 2>&1; grep -v linear $OUT/stamps.log
+fi

@@ -20,7 +20,7 @@ fi
 if [ "$SKIP_NCU" != "1" ]; then
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-train-step --no-torch-gpu-baseline --no-strong-scaling --no-carla > $OUT/ncu_launch_bench.log 2>&1; echo "ncu launches exit $?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"${NCU_KERNELS:-attn_fused_kernel|linear_tc_kernel|mlp_chain_kernel}" -s 40 -c 4 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"${NCU_KERNELS:-attn_fused_kernel|mlp_chain_kernel}" -s 40 -c 4 \
     -o $OUT/prof_top python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-train-step --no-torch-gpu-baseline --no-strong-scaling --no-carla > $OUT/ncu_full.log 2>&1; echo "ncu full exit $?"
 fi
 if [ "$SKIP_SAN" != "1" ]; then bash tools/gpu_sanitize.sh $TAG/san; fi

@@ -33,6 +33,6 @@ for prec, mode in ((1, 1), (1, 2), (2, 1)):
         e1.record(); torch.cuda.synchronize()
     buf=(ctypes.c_longlong*16)()
     h.o4d_debug_read(buf); v=list(buf)
-    print('prec %d mode %d: %.3f ms/batch; fused stamps: start->loop %d, loop %d, loop_end->acc2 %d, epilogue %d, total %d' % (prec, mode, e0.elapsed_time(e1)/5, v[0]-v[4], v[1]-v[0], v[2]-v[1], v[3]-v[2], v[3]-v[4])); print('   epilogue parts: acc1 wait %d, stage %d, barriers %d, reduce %d, issue_v %d' % (v[5],v[6],v[7],v[8],v[9]))
-    h.o4d_debug_read_tc(buf); v=list(buf)  # per-layer kernel (not on the chain path)
-    print('   linear stamps: loop %d, wait accum %d, epilogue %d' % (v[1]-v[0], v[2]-v[1], v[3]-v[2]))
+    print('prec %d mode %d: %.3f ms/batch; fused stamps: start->loop %d, loop %d, loop_end->acc2 %d, epilogue %d, total %d' % (prec, mode, e0.elapsed_time(e1)/5, v[0]-v[4], v[1]-v[0], v[2]-v[1], v[3]-v[2], v[3]-v[4])); print('   epilogue parts: acc1 wait %d, stage %d, barriers %d, reduce %d, issue_v %d' % (v[5],v[6],v[7],v[8],v[9])); print('   conversion loop of thread 0 (13 chunks of its group): loop top (G_EMPTY wait + gather issue) %d, wait ACC1_FULL %d, tmem ld + gather wait + LDS %d, relu/split %d, tmem st + arrive %d' % (v[10],v[11],v[12],v[13],v[14]))
+    h.o4d_debug_read_chain(buf); v=list(buf)   # last chain launch of the mini-batch (layer3 .. lin_out), one CTA
+    print('   chain (last launch): MMA thread total %d cycles for %d items: waits acc-empty %d (epilogue-bound), full-stage %d (load-bound); producer waits: empty-stage %d (MMA-bound), dependency %d; epilogue warp 0: wait %d busy %d' % (v[0], v[7], v[1], v[2], v[3], v[4], v[5], v[6]))

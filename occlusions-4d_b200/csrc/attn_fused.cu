@@ -61,7 +61,7 @@ constexpr int G_PITCH = 144;
 constexpr int G_ROWS = BM + 16;              // 128 Ka rows + up to 16 Qa rows (k >= 8)
 constexpr int G_STAGE = G_ROWS * G_PITCH;    // 20,736 B
 constexpr int G_STAGES = 2;                  // per group; group 1's pair lives in the (idle during the main loop) hidden-buffer region
-constexpr int BAR_BYTES = 320;               // 34 mbarriers + the TMEM slot
+constexpr int BAR_BYTES = 320;               // 31 mbarriers + the TMEM slot
 constexpr int TAIL_BYTES = BAR_BYTES + BM * 4;   // then the tile's neighbour ids
 
 __host__ __device__ inline int w2_bytes(int d) { return 2 * d * 32 * 2; }             // W_a2 chunk, hi + lo
@@ -256,7 +256,6 @@ struct Params {
     float* out;                            // (n, d)
     int64_t n;
     int d, k, tq, split;
-    int issue_mode;                        // MMA1(c) waits for MMA2(c - 3): 1 = to be issued (default), 0 = to complete
     float scale_log2;                      // log2(e) / sqrt(d): softmax evaluated with exp2
 };
 
@@ -274,7 +273,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fused_kernel(const Params p) 
     const int OFF_G = off_g(d);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_G + G_STAGES * G_STAGE);
     enum { W_FULL = 0, W_EMPTY = 2, WC_FULL = 4, WC_EMPTY = 8, ACC1_FULL = 12, A2_FULL = 15, A2_EMPTY = 18,
-           R_READY = 21, ACC2_FULL = 22, G_FULL = 23, G_EMPTY = 27, A2_ISSUED = 31, NBARS = 34 };   // G_*: [group][stage]
+           R_READY = 21, ACC2_FULL = 22, G_FULL = 23, G_EMPTY = 27, NBARS = 31 };   // G_*: [group][stage]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBARS);
     int32_t* s_j = reinterpret_cast<int32_t*>(smem + OFF_G + G_STAGES * G_STAGE + BAR_BYTES);   // neighbour id per tile row
     const uint32_t bar0 = smem_u32(bars);
@@ -290,7 +289,6 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fused_kernel(const Params p) 
             mbar_init(BAR(ACC1_FULL + i), 1);
             mbar_init(BAR(A2_FULL + i), GROUP_WARPS);     // a chunk is converted (or drained) by ONE group
             mbar_init(BAR(A2_EMPTY + i), 1);
-            mbar_init(BAR(A2_ISSUED + i), 1);
         }
         mbar_init(BAR(R_READY), GROUP_WARPS);             // group 0 builds the r operand
         mbar_init(BAR(ACC2_FULL), 1);
@@ -533,9 +531,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fused_kernel(const Params p) 
                 tc_fence_after();
                 mma2(c);
                 umma_commit(BAR(W_EMPTY + (c & 1)));
-                umma_commit(BAR(A2_EMPTY + c % NBUF));          // completion: acc1[c % 3] has been read (delta phase, issue_mode 0)
-                tc_fence_before();                              // order the queued MMAs before the cross-thread signal
-                mbar_arrive(BAR(A2_ISSUED + c % NBUF));         // issue: MMA2(c) is in the tensor pipe's queue (see the MMA1 warp)
+                umma_commit(BAR(A2_EMPTY + c % NBUF));          // acc1[c % 3] may be overwritten by MMA1(c + 3)
             }
             umma_commit(BAR(ACC2_FULL));
         }
@@ -569,18 +565,15 @@ __global__ void __launch_bounds__(THREADS, 1) attn_fused_kernel(const Params p) 
             };
             mbar_wait(BAR(R_READY), 0);
             tc_fence_after();
-            // MMA1(c) overwrites acc1[c % 3], which MMA2(c - 3) reads as its A operand.  The tensor pipe executes in issue
-            // order, so MMA1(c) only has to be ISSUED after MMA2(c - 3) -- it need not wait for its completion
-            // (issue_mode 1, default: the MMA2 thread arrives on A2_ISSUED right after queueing MMA2(c - 3)).  Waiting
-            // for the completion instead (issue_mode 0, A2_EMPTY) queued MMA1(c) BEHIND MMA2(c - 2), so the conversion
-            // of chunk c could start only one MMA2 later and the loop period became MMA1 + the conversion latency
-            // (~1.3 k cycles per chunk for ANY number of MMA2 passes: 38.8 k / 34.1 k / 32.7 k cycles per tile with
-            // 3 / 2 / 1 passes, in-kernel stamps) instead of the MMA2 time.  (One thread issuing both in program order is
-            // correct as well but serialises the issue and the waits: 44.5 k.)
-            const bool by_issue = p.issue_mode == 1;
+            // MMA1(c) overwrites acc1[c % 3], which MMA2(c - 3) read as its A operand: wait for its completion.
+            // (Tried, measured, not kept -- profiles/r2_c_*: (i) ordering MMA1(c) only behind the ISSUE of MMA2(c - 3)
+            // through a flag, relying on the in-order tensor pipe: correct, same speed, because the MMA2 thread queues
+            // MMA2(c - 2) before this thread wakes up; (ii) ONE thread issuing MMA2(c), MMA1(c + 3) in program order:
+            // correct, but the ~50 cycles of issue per tcgen05 instruction and the waits then serialise, 44.5 k instead
+            // of 34 k cycles per tile.)
             for (int c = 0; c < NC; ++c) {
                 mbar_wait(BAR(WC_FULL + c % WC_STAGES), (uint32_t)(c / WC_STAGES) & 1u);
-                if (c >= NBUF) mbar_wait(BAR((by_issue ? A2_ISSUED : A2_EMPTY) + c % NBUF), (uint32_t)(c / NBUF - 1) & 1u);
+                if (c >= NBUF) mbar_wait(BAR(A2_EMPTY + c % NBUF), (uint32_t)(c / NBUF - 1) & 1u);   // MMA2(c - 3) retired
                 tc_fence_after();
                 mma1(c);
                 umma_commit(BAR(ACC1_FULL + c % NBUF));
@@ -842,14 +835,6 @@ int attn_fused_launch(const PtBlockParams& P, const AttnTables& T, const float* 
         int mode = g_fused_mma2_mode.load(std::memory_order_relaxed);
         if (mode == 0) mode = fused_mode_default();
         p.split = (precision == 1) ? mode : 0;
-    }
-    {
-        static int im = -1;
-        if (im < 0) {
-            const char* e = getenv("O4D_FUSED_ISSUE");          // 0 = MMA1 waits for MMA2's completion (A/B timing)
-            im = (e && e[0] == '0') ? 0 : 1;
-        }
-        p.issue_mode = im;
     }
     p.scale_log2 = (float)(1.4426950408889634 / sqrt((double)d));
     const int64_t tiles = cdiv(n, p.tq);

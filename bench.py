@@ -705,6 +705,32 @@ def run_o4d(args):
         e1.record()
         torch.cuda.synchronize()
         enc_ms = e0.elapsed_time(e1) / enc_iters
+        # the encoder's critical path: the serial arg-max chain of farthest point sampling (torch_cluster.fps semantics,
+        # modules.py:133) over the level pyramid, timed on its own -- a latency bound, not a bandwidth / tensor one
+        fps_chain = None
+        try:
+            sizes, nl = [], cfg['n_points']
+            for _ in range(cfg['pcl_args']['down_blocks']):
+                nn = -(-nl // cfg['pcl_args']['transition_factor'])
+                sizes.append((nl, nn))
+                nl = nn
+            clouds = [pcl[:a, :3].contiguous() for a, _ in sizes]
+            for c_, (a, b) in zip(clouds, sizes):
+                ops.fps(c_, b, 0)
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(3):
+                for c_, (a, b) in zip(clouds, sizes):
+                    ops.fps(c_, b, 0)
+            f1.record()
+            torch.cuda.synchronize()
+            fps_ms = f0.elapsed_time(f1) / 3
+            picks = sum(b for _, b in sizes)
+            fps_chain = {'bound': 'latency (serial arg-max chain)', 'picks': picks, 'ms': fps_ms,
+                         'us_per_pick': fps_ms * 1e3 / picks, 'share_of_encoder': fps_ms / enc_ms,
+                         'levels': [list(x) for x in sizes]}
+        except Exception as exc:               # noqa: BLE001
+            fps_chain = {'error': '%s: %s' % (type(exc).__name__, exc)}
         abstract, glob = abstract[0].contiguous(), glob[0].contiguous()
         scene = dec.o4d_scene(abstract, glob)
         dcfg, dparams = dec.o4d_config(), dec.o4d_params()
@@ -830,7 +856,7 @@ def run_o4d(args):
                 'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'kernel_families': families,
                 'cpu_baseline': cpu_base, 'torch_gpu_baseline': torch_gpu,
                 'encoder': {'pts_per_s': cfg['n_points'] / (enc_ms / 1e3), 'ms': enc_ms, 'n_points': cfg['n_points'],
-                            'reference': enc_base},
+                            'critical_path': fps_chain, 'reference': enc_base},
                 'carla_config3': carla, 'strong_scaling': strong, 'second_device_in_process': second_dev,
                 'train_step': train, 'tcgen05': bool(lib.o4d_has_tcgen05())}
         print(json.dumps(line))

@@ -14,8 +14,12 @@
  *     leading dimension (ld*, in elements) where a view can be strided;
  *   - neighbour / sample indices are int64 at this boundary (the reference hands out
  *     torch.int64) and int32 inside;
- *   - no allocation and no host synchronisation inside compute calls: scratch memory
- *     is caller-owned (query the size with the matching *_workspace_bytes call);
+ *   - no host synchronisation inside compute calls; scratch memory is caller-owned (query the size with the matching
+ *     *_workspace_bytes call).  One exception to "no allocation": a dense layer given an UN-packed fp32 weight on the
+ *     tensor-core path (o4d_linear_f32, and the dense layers inside o4d_encoder_forward / the o4d_*_train entries)
+ *     packs it into a stream-ordered temporary (cudaMallocAsync / cudaFreeAsync on `stream`: pool reuse after the
+ *     first call, no device synchronisation).  The decoder keeps its images in the scene buffer, and
+ *     o4d_linear_pack_f32 / o4d_linear_packed_f32 give every other caller the allocation-free form;
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
  *   - every function returns 0 on success, <0 for an invalid argument (O4D_E_*), >0 for
  *     a cudaError_t raised by a launch; o4d_last_error() gives a message for the
@@ -98,6 +102,20 @@ int o4d_linear_f32(const float* A, int64_t rows, int64_t k, int64_t lda,
                    const float* W, const float* bias, int64_t n,
                    const float* R, int64_t ldr,
                    float* C, int64_t ldc, int flags, int precision, void* stream);
+
+/* The same layer with a CALLER-OWNED packed weight: o4d_linear_f32 converts W into its tensor-core image (bf16 hi/lo,
+ * shared-memory layout) in a stream-ordered temporary on every call (the only compute entry that allocates); callers that
+ * reuse a weight pack it once and keep the image next to it, re-packing when the weight changes:
+ *     bytes = o4d_linear_pack_bytes(rows, k, n, precision)   0: this shape / precision runs on CUDA cores, use o4d_linear_f32
+ *     o4d_linear_pack_f32(W, n, k, ldw, packed, stream)       W (n, k) row-major with leading dimension ldw
+ *     o4d_linear_packed_f32(A, ..., packed, ...)              same arguments and semantics as o4d_linear_f32
+ * (o4d/ops.py keeps such a cache per (weight storage, version); the decoder keeps its images in the scene buffer.) */
+size_t o4d_linear_pack_bytes(int64_t rows, int64_t k, int64_t n, int precision);
+int o4d_linear_pack_f32(const float* W, int64_t n, int64_t k, int64_t ldw, void* packed, void* stream);
+int o4d_linear_packed_f32(const float* A, int64_t rows, int64_t k, int64_t lda,
+                          const void* packed, const float* bias, int64_t n,
+                          const float* R, int64_t ldr,
+                          float* C, int64_t ldc, int flags, int precision, void* stream);
 
 /* ------------------------------------------------------------------ Fourier features
  * positional_encode, model/implicit.py:20-43 with base_frequency 0.1 (:184,:405):

@@ -51,9 +51,24 @@ __device__ __forceinline__ void st_remote_u64_addr(uint32_t ra, uint64_t v) {
 }
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint64_t ld_volatile_shared_u64(const void* p) {
+    uint64_t v;
+    asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+// Candidate word: [63:32] running-min distance bits, [31:18] pick tag ((pick + 1) mod 2^14), [17:0] point index.
+constexpr uint32_t IDX_BITS = 18, IDX_MASK = (1u << IDX_BITS) - 1u, TAG_MASK = 0x3fffu;
+
 // CTAS = cluster size (launch attribute), P = points per thread; points are dealt out round-robin over all
 // CTAS * THREADS threads of the cluster.
-template <int CTAS, int P>
+// POLL (round 2, default): no cluster barrier inside the pick loop.  Every candidate word carries the tag of its pick;
+// a thread spins on the CTAS slots of its own shared memory until all of them show the current tag.  The exchange then
+// costs one remote 8-byte store plus its flight time instead of a hardware cluster barrier of 8 x 512 threads
+// (arrive.release / wait.acquire), which was most of the 0.99 us per pick.  Slots are double buffered by pick parity:
+// a CTA can write slot parity p of pick i + 2 only after it has seen every candidate of pick i + 1, which every CTA
+// published after its last read of pick i -- so no slot is overwritten while still being read, and a stale word (pick
+// i - 2, same parity) never matches the tag.
+template <int CTAS, int P, bool POLL>
 __global__ void __launch_bounds__(THREADS, 1)
 fps_cluster_kernel(const float* __restrict__ xyz, int n, int64_t ld, int n_out, int start,
                    int32_t* __restrict__ counts,   // (n) zero-initialised
@@ -70,6 +85,7 @@ fps_cluster_kernel(const float* __restrict__ xyz, int n, int64_t ld, int n_out, 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t rank = cluster_ctarank();
 
+    if (tid < 2 * NCAND) (&s_cand[0][0])[tid] = 0ull;
     for (int j = tid; j < n; j += THREADS) {
         sx[j] = xyz[(int64_t)j * ld + 0];
         sy[j] = xyz[(int64_t)j * ld + 1];
@@ -140,30 +156,57 @@ fps_cluster_kernel(const float* __restrict__ xyz, int n, int64_t ld, int n_out, 
             }
             v = __shfl_sync(0xffffffffu, v, 0);
             i = __shfl_sync(0xffffffffu, i, 0);
-            if (lane < CTAS) st_remote_u64_addr(r_cand[par], ((uint64_t)__float_as_uint(v) << 32) | (uint32_t)i);
+            // (a CTA without points publishes value -1 and the sentinel index: masked, so that it cannot spill into the tag)
+            const uint32_t tagged = POLL ? ((((uint32_t)it + 1u) & TAG_MASK) << IDX_BITS) | ((uint32_t)i & IDX_MASK) : (uint32_t)i;
+            if (lane < CTAS) st_remote_u64_addr(r_cand[par], ((uint64_t)__float_as_uint(v) << 32) | tagged);
         }
-        cluster_arrive();       // release: the remote stores above are visible after the matching wait
-        cluster_wait();
         float gv = -2.f;
         int gi = 0x7fffffff;
+        if (POLL) {
+            const uint32_t tag = ((uint32_t)it + 1u) & TAG_MASK;
+            uint64_t e[NCAND];
+            bool ok;
+            long long t0 = 0;
+            do {
+                ok = true;
 #pragma unroll
-        for (int c = 0; c < NCAND; ++c) {
-            const uint64_t e = s_cand[par][c];
-            argmax_combine(gv, gi, __uint_as_float((uint32_t)(e >> 32)), (int)(uint32_t)(e & 0xffffffffu));
+                for (int c = 0; c < NCAND; ++c) {
+                    e[c] = ld_volatile_shared_u64(&s_cand[par][c]);
+                    ok = ok && ((((uint32_t)e[c]) >> IDX_BITS) == tag);
+                }
+                if (!ok) {                                   // bounded: a protocol bug fails the launch instead of hanging
+                    if (t0 == 0) t0 = clock64();
+                    else if (clock64() - t0 > 2000000000LL) __trap();
+                }
+            } while (!ok);
+#pragma unroll
+            for (int c = 0; c < NCAND; ++c)
+                argmax_combine(gv, gi, __uint_as_float((uint32_t)(e[c] >> 32)), (int)((uint32_t)e[c] & IDX_MASK));
+        } else {
+            cluster_arrive();       // release: the remote stores above are visible after the matching wait
+            cluster_wait();
+#pragma unroll
+            for (int c = 0; c < NCAND; ++c) {
+                const uint64_t e = s_cand[par][c];
+                argmax_combine(gv, gi, __uint_as_float((uint32_t)(e >> 32)), (int)(uint32_t)(e & 0xffffffffu));
+            }
         }
         cur = gi;
         // s_val / s_idx are rewritten only after the next distance update and s_cand[parity] only two
-        // picks later, both separated from these reads by a cluster barrier.
+        // picks later (see POLL above / separated from these reads by a cluster barrier).
     }
+    // no CTA may exit while a peer can still store into its shared memory
+    cluster_arrive();
+    cluster_wait();
 }
 
 }  // namespace fc
 
 // Returns O4D_E_UNSUPPORTED when the cloud does not fit this kernel (the caller falls back).
-template <int CTAS, int P>
+template <int CTAS, int P, bool POLL>
 static int fps_cluster_launch_t(const float* xyz, int64_t n, int64_t ld, int64_t n_out, int64_t start, int32_t* counts,
                                 int64_t* order64, size_t smem, cudaStream_t st) {
-    O4D_SMEM_ATTR((fc::fps_cluster_kernel<CTAS, P>), 200 * 1024);
+    O4D_SMEM_ATTR((fc::fps_cluster_kernel<CTAS, P, POLL>), 200 * 1024);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(CTAS, 1, 1);
     cfg.blockDim = dim3(fc::THREADS, 1, 1);
@@ -176,7 +219,7 @@ static int fps_cluster_launch_t(const float* xyz, int64_t n, int64_t ld, int64_t
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    O4D_CUDA(cudaLaunchKernelEx(&cfg, fc::fps_cluster_kernel<CTAS, P>, xyz, (int)n, ld, (int)n_out, (int)start, counts, order64));
+    O4D_CUDA(cudaLaunchKernelEx(&cfg, fc::fps_cluster_kernel<CTAS, P, POLL>, xyz, (int)n, ld, (int)n_out, (int)start, counts, order64));
     count_launch();
     return 0;
 }
@@ -185,14 +228,25 @@ int fps_cluster_launch(const float* xyz, int64_t n, int64_t ld, int64_t n_out, i
                        int64_t* order64, cudaStream_t st) {
     const size_t smem = (size_t)3 * n * sizeof(float);
     if (n <= 2048 || smem > 200 * 1024) return O4D_E_UNSUPPORTED;
-    static int ctas = 0;
-    if (ctas == 0) {
-        const char* e = getenv("O4D_FPS_CTAS");          // cluster size: 2, 4 or 8 (default)
-        ctas = e ? atoi(e) : 8;
-        if (ctas != 2 && ctas != 4) ctas = 8;
+    static int ctas_env = -1;
+    if (ctas_env < 0) {
+        const char* e = getenv("O4D_FPS_CTAS");          // force a cluster size: 2, 4 or 8
+        ctas_env = e ? atoi(e) : 0;
+        if (ctas_env != 2 && ctas_env != 4 && ctas_env != 8) ctas_env = 0;
     }
+    // measured per pick with the polled exchange (profiles/r2_g_fps_timing.txt): N = 14336: 0.89 us on 8 CTAs, 0.87 on 4,
+    // 0.99 on 2; N = 4779: 0.85 / 0.76 / 0.79 -> 8 CTAs above 8192 points, 4 below
+    const int ctas = ctas_env ? ctas_env : (n > 8192 ? 8 : 4);
+    static int poll = -1;
+    if (poll < 0) {
+        const char* e = getenv("O4D_FPS_SYNC");          // "barrier" = hardware cluster barrier per pick (A/B timing)
+        poll = (e && e[0] == 'b') ? 0 : 1;
+    }
+    if (n > (int64_t)fc::IDX_MASK) poll = 0;             // the tagged candidate word holds 18 index bits
     const int ppt = (int)cdiv(n, (int64_t)ctas * fc::THREADS);
-#define O4D_FC(C, PV) return fps_cluster_launch_t<C, PV>(xyz, n, ld, n_out, start, counts, order64, smem, st)
+#define O4D_FC(C, PV)                                                                                            \
+    return poll ? fps_cluster_launch_t<C, PV, true>(xyz, n, ld, n_out, start, counts, order64, smem, st)        \
+                : fps_cluster_launch_t<C, PV, false>(xyz, n, ld, n_out, start, counts, order64, smem, st)
     if (ctas == 8) {
         if (ppt <= 1) O4D_FC(8, 1);
         if (ppt <= 2) O4D_FC(8, 2);

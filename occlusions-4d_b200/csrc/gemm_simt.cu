@@ -168,3 +168,32 @@ extern "C" int o4d_linear_f32(const float* A, int64_t rows, int64_t k, int64_t l
     return o4d::linear_launch(A, rows, k, lda, W, bias, n, R, ldr, C, ldc, flags, precision,
                               (cudaStream_t)stream);
 }
+
+// ---- caller-owned packed weights (no allocation, no re-packing inside the compute call) ----------------------------
+extern "C" size_t o4d_linear_pack_bytes(int64_t rows, int64_t k, int64_t n, int precision) {
+    if (precision == 0 || !o4d::tc_shape_ok(rows, k, n)) return 0;      // this shape runs on the CUDA-core kernel: nothing to pack
+    return o4d::tc_pack_bytes(n, k);
+}
+
+extern "C" int o4d_linear_pack_f32(const float* W, int64_t n, int64_t k, int64_t ldw, void* packed, void* stream) {
+    using namespace o4d;
+    O4D_REQUIRE(W && packed && n >= 1 && k >= 1 && ldw >= k, "linear pack: bad argument");
+    return tc_pack_launch(W, n, k, ldw, packed, (cudaStream_t)stream);
+}
+
+extern "C" int o4d_linear_packed_f32(const float* A, int64_t rows, int64_t k, int64_t lda, const void* packed,
+                                     const float* bias, int64_t n, const float* R, int64_t ldr, float* C, int64_t ldc,
+                                     int flags, int precision, void* stream) {
+    using namespace o4d;
+    O4D_REQUIRE(A && packed && C, "linear (packed): null pointer");
+    O4D_REQUIRE(rows >= 0 && k >= 1 && n >= 1 && lda >= k && ldc >= n && (!R || ldr >= n), "linear (packed): bad shape");
+    O4D_REQUIRE(precision == 1 || precision == 2, "linear (packed): the packed form is the tcgen05 path (precision 1 or 2)");
+    if (!tc_shape_ok(rows, k, n)) {
+        set_error("linear (packed): shape (%lld, %lld, %lld) is not on the tensor-core path (o4d_linear_pack_bytes == 0)",
+                  (long long)rows, (long long)k, (long long)n);
+        return O4D_E_UNSUPPORTED;
+    }
+    if (rows == 0) return 0;
+    ProfScope prof(PROF_LINEAR, 2.0 * (double)rows * (double)k * (double)n, (cudaStream_t)stream);
+    return linear_tc_packed_launch(A, rows, k, lda, packed, n, bias, R, ldr, C, ldc, flags, precision, (cudaStream_t)stream);
+}

@@ -216,11 +216,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const Program P) 
                                 for (int e = 0; e < 4; ++e) {
                                     float x0 = v[h8 * 8 + 2 * e] + b8[2 * e], x1 = v[h8 * 8 + 2 * e + 1] + b8[2 * e + 1];
                                     if (relu_img) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
-                                    __nv_bfloat16 h0, l0, h1, l1;
-                                    split_bf16(x0, h0, l0);
-                                    split_bf16(x1, h1, l1);
-                                    hi[e] = pack2(h0, h1);
-                                    lo[e] = pack2(l0, l1);
+                                    split_bf16x2(x0, x1, hi[e], lo[e]);
                                 }
                                 uint8_t* dst = img_row + (size_t)(gc >> 5) * IMG_CHUNK_BYTES + ((gc & 31) >> 3) * (BM * 16);
                                 *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -258,12 +254,12 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const Program P) 
                                     if (op.out && row < rows_here) *reinterpret_cast<float4*>(op.out + (row0 + row) * op.ldo + gc) = x;
                                     if (op.img) {
                                         if (relu_img) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
-                                        __nv_bfloat16 h0, l0, h1, l1, h2, l2, h3, l3;
-                                        split_bf16(x.x, h0, l0); split_bf16(x.y, h1, l1);
-                                        split_bf16(x.z, h2, l2); split_bf16(x.w, h3, l3);
+                                        uint32_t h01, l01, h23, l23;
+                                        split_bf16x2(x.x, x.y, h01, l01);
+                                        split_bf16x2(x.z, x.w, h23, l23);
                                         uint8_t* dst = img_rows + it * 128 + img_col;
-                                        *reinterpret_cast<uint2*>(dst) = make_uint2(pack2(h0, h1), pack2(h2, h3));
-                                        *reinterpret_cast<uint2*>(dst + A_HALF) = make_uint2(pack2(l0, l1), pack2(l2, l3));
+                                        *reinterpret_cast<uint2*>(dst) = make_uint2(h01, h23);
+                                        *reinterpret_cast<uint2*>(dst + A_HALF) = make_uint2(l01, l23);
                                     }
                                 }
                             }
@@ -292,9 +288,12 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const Program P) 
                         if (PAIR && rank != 0) mbar_arrive_cluster(acce0 + 8 * acc, 0);   // the leader's MMA thread waits for both CTAs
                         else mbar_arrive(acce0 + 8 * acc);
                     }
-                    // this warp's part of the item is in global memory: make it visible to the TMA engine (async
-                    // proxy) of this CTA before the producer is told (generic stores -> fence -> flag)
-                    __threadfence();
+                    // this warp's part of the item is in global memory: order it before the TMA engine's (async proxy)
+                    // reads of this CTA's producer: generic stores -> fence.proxy.async (every writing lane) -> warp
+                    // barrier -> release store of the progress flag; the producer acquires the flag, then issues the copy.
+                    // (A gpu-scope __threadfence() in front of the proxy fence showed up as 17 % of all warp stall samples
+                    // in ncu -- "membar" -- and is not needed: writer and reader are the same CTA.)
+                    if (P.fence_gpu) __threadfence();
                     fence_proxy_async_all();
                     __syncwarp();
                     if (lane == 0) st_release_shared(done0 + 4 * warp, item + 1);
@@ -485,11 +484,7 @@ __global__ void image_from_f32_kernel(const float* __restrict__ src, int64_t ld,
         for (int e = 0; e < 4; ++e) {
             float x0 = v[2 * e], x1 = v[2 * e + 1];
             if (relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
-            __nv_bfloat16 h0, l0, h1, l1;
-            split_bf16(x0, h0, l0);
-            split_bf16(x1, h1, l1);
-            hi[e] = pack2(h0, h1);
-            lo[e] = pack2(l0, l1);
+            split_bf16x2(x0, x1, hi[e], lo[e]);
         }
         uint8_t* dst = img + img_off(tile, cpt, trow, gc);
         *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -569,6 +564,14 @@ int mlp_chain_launch(mc::Program& prog, cudaStream_t st) {
                     "mlp chain: layer %d writes an image next to an unaligned fp32 output", o);
         op.n_img = op.img ? op.img_cpt * 32 : 0;
         flops += 2.0 * (double)prog.rows * op.k_alg * op.n;
+    }
+    {
+        static int fg = -1;
+        if (fg < 0) {
+            const char* e = getenv("O4D_CHAIN_FENCE_GPU");      // 1 = gpu-scope fence before the proxy fence (A/B, paranoia)
+            fg = (e && e[0] == '1') ? 1 : 0;
+        }
+        prog.fence_gpu = fg;
     }
     ProfScope prof(PROF_LINEAR, flops, st);
     if (mlp_chain_pair()) {

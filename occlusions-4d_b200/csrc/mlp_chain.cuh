@@ -34,6 +34,7 @@ struct Program {
     int nops;
     int tiles;
     int split;             // 1: bf16x3, 0: single bf16 pass
+    int fence_gpu;         // 1: gpu-scope fence in front of the epilogue's proxy fence (diagnostic)
     int64_t rows;
 };
 

@@ -96,6 +96,17 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
     lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
 
+// Two values at once: ONE packing convert (F2FP.BF16.F32.PACK_AB, full rate) per pair and image half instead of two
+// scalar F2F conversions (quarter-rate conversion pipe); the bf16 -> fp32 back-conversion is a shift / a mask.
+// Same round-to-nearest-even results as split_bf16.  Low 16 bits = a, high 16 bits = b.
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi2, uint32_t& lo2) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    hi2 = *reinterpret_cast<const uint32_t*>(&h);
+    const float ha = __uint_as_float(hi2 << 16), hb = __uint_as_float(hi2 & 0xffff0000u);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(a - ha, b - hb);
+    lo2 = *reinterpret_cast<const uint32_t*>(&l);
+}
+
 // ---- CTA pairs (cluster of two, tcgen05 cta_group::2): the leader CTA (cluster rank 0) issues M = 256 MMAs whose rows
 // 0-127 accumulate in its own tensor memory and rows 128-255 in the peer's; each CTA supplies its own A rows and HALF
 // of the B rows from its shared memory.

@@ -45,6 +45,10 @@ SIGNATURES = {
     'o4d_fps_f32': (c_int, [c_ptr, c_i64, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_size, c_ptr]),
     'o4d_linear_f32': (c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_i64,
                                c_int, c_int, c_ptr]),
+    'o4d_linear_pack_bytes': (c_size, [c_i64, c_i64, c_i64, c_int]),
+    'o4d_linear_pack_f32': (c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr]),
+    'o4d_linear_packed_f32': (c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_i64,
+                                      c_int, c_int, c_ptr]),
     'o4d_resblock_workspace_bytes': (c_size, [c_i64, c_int, c_int]),
     'o4d_resblock_forward_f32': (c_int, [c_ptr, c_i64, c_int, c_i64, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_i64,
                                          c_int, c_ptr, c_size, c_ptr]),

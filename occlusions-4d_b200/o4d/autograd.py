@@ -46,9 +46,9 @@ class LinearFn(torch.autograd.Function):
             # rejects in-place writes to views made inside a custom Function)
             y = torch.empty((*lead, n), dtype=torch.float32, device=x2.device)
             if x2.shape[0] > 0:        # an empty batch has no device pointers to hand over
-                rc = _lib.lib().o4d_linear_f32(_ptr(x2), x2.shape[0], k, k, _ptr(w), _ptr(b), n, _ptr(r), n,
-                                               _ptr(y), n, flags, prec, _stream(x2))
-                _lib.check(rc, 'o4d_linear_f32')
+                # packed-weight cache keyed on (storage, version): a weight is packed once per optimizer step, not
+                # once per call (4 decoder frames per training step share every weight)
+                ops.linear_call(x2, k, w, b, r, n, y.reshape(-1, n), flags, prec)
         assert not (relu_out and residual is not None), 'linear: relu_out with a residual is not used on the path'
         ctx.save_for_backward(x2, w, y if relu_out else None)
         ctx.meta = (lead, relu_in, relu_out, prec, bias is not None, residual is not None)

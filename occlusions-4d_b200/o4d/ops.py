@@ -4,6 +4,7 @@ PyTorch is used for device memory, streams and module plumbing only; every arith
 operation below runs in libo4d.so.  All inputs must be CUDA fp32 tensors -- there is no
 CPU path.
 """
+import collections
 import ctypes
 
 import torch
@@ -119,6 +120,45 @@ def fps(xyz, n_out, start_idx=0, return_order=False):
 
 # ---------------------------------------------------------------------------- dense layer
 
+# Caller-owned tensor-core images of weights (o4d_linear_pack_f32): one per (weight storage, version, shape, device),
+# re-packed when the weight is updated in place (optimizer step) or replaced; bounded, least recently used first out.
+_PACKED = collections.OrderedDict()
+_PACKED_MAX = 512
+
+
+def packed_weight(w, nbytes):
+    """bf16 hi/lo image of the contiguous fp32 weight `w` (n, k), cached on (data_ptr, _version)."""
+    key = (w.data_ptr(), w._version, tuple(w.shape), w.device.index)
+    hit = _PACKED.get(key)
+    if hit is not None:
+        _PACKED.move_to_end(key)
+        return hit[0]
+    buf = torch.empty(int(nbytes), dtype=torch.uint8, device=w.device)
+    rc = _lib.lib().o4d_linear_pack_f32(_ptr(w), w.shape[0], w.shape[1], w.shape[1], _ptr(buf), _stream(w))
+    _lib.check(rc, 'o4d_linear_pack_f32')
+    # the weight tensor is kept alive with the entry: its address cannot be recycled for another weight meanwhile
+    _PACKED[key] = (buf, w)
+    while len(_PACKED) > _PACKED_MAX:
+        _PACKED.popitem(last=False)
+    return buf
+
+
+def linear_call(a, lda, w, b, r, ldr, c, flags, prec):
+    """One dense layer through the C ABI: the packed form (cached image, no allocation inside the call) whenever the
+    shape is on the tensor-core path, o4d_linear_f32 otherwise."""
+    L = _lib.lib()
+    n, k = w.shape
+    nbytes = L.o4d_linear_pack_bytes(a.shape[0], k, n, prec) if a.shape[0] > 0 else 0
+    if nbytes:
+        rc = L.o4d_linear_packed_f32(_ptr(a), a.shape[0], k, lda, _ptr(packed_weight(w, nbytes)), _ptr(b), n, _ptr(r),
+                                     ldr or 0, _ptr(c), n, flags, prec, _stream(a))
+        _lib.check(rc, 'o4d_linear_packed_f32')
+    else:
+        rc = L.o4d_linear_f32(_ptr(a), a.shape[0], k, lda, _ptr(w), _ptr(b), n, _ptr(r), ldr or 0, _ptr(c), n, flags, prec,
+                              _stream(a))
+        _lib.check(rc, 'o4d_linear_f32')
+
+
 def linear(x, weight, bias=None, residual=None, relu_in=False, relu_out=False, precision=None, out=None):
     """post(pre(x) @ weight.T + bias) [+ residual] over the last dimension of x."""
     x = _f32(x, 'x')
@@ -135,9 +175,7 @@ def linear(x, weight, bias=None, residual=None, relu_in=False, relu_out=False, p
         c = out if out is not None else torch.empty((a.shape[0], n), dtype=torch.float32, device=a.device)
         flags = (RELU_IN if relu_in else 0) | (RELU_OUT if relu_out else 0)
         prec = default_precision() if precision is None else int(precision)
-        rc = _lib.lib().o4d_linear_f32(_ptr(a), a.shape[0], k, lda, _ptr(w), _ptr(b), n, _ptr(r), ldr or 0,
-                                       _ptr(c), n, flags, prec, _stream(a))
-    _lib.check(rc, 'o4d_linear_f32')
+        linear_call(a, lda, w, b, r, ldr, c, flags, prec)
     return c.reshape(*lead, n)
 
 

@@ -173,6 +173,26 @@ def test_fused_residual_block_matches_fp64(rows, d, dh):
                         b1.to(DEV)[:40].contiguous(), precision=1) is None      # width 40: not a whole image chunk
 
 
+def test_linear_packed_weight_cache_follows_in_place_updates():
+    """o4d.ops keeps the tensor-core image of a weight (o4d_linear_pack_f32 / o4d_linear_packed_f32: no allocation or
+    re-packing inside the compute call) keyed on (storage, version): an optimizer-style in-place update must re-pack."""
+    g = torch.Generator().manual_seed(4)
+    w = (torch.randn(416, 416, generator=g) / 20.0).to(DEV)
+    a = torch.randn(2000, 416, generator=g).to(DEV)
+    y1 = ops.linear(a, w, precision=1)
+    entries = len(ops._PACKED)
+    assert entries >= 1
+    assert torch.equal(ops.linear(a, w, precision=1), y1) and len(ops._PACKED) == entries      # cache hit
+    want = a.cpu().double() @ w.cpu().double().t()
+    assert relerr(y1.cpu().double(), want) < TOL_SPLIT
+    w.mul_(-2.0)                                                                               # version bump, same storage
+    y2 = ops.linear(a, w, precision=1)
+    assert len(ops._PACKED) == entries + 1
+    assert relerr(y2.cpu().double(), -2.0 * want) < TOL_SPLIT
+    # a shape below the tensor-core threshold packs nothing and still works
+    assert relerr(ops.linear(a[:100], w, precision=1).cpu().double(), -2.0 * want[:100]) < TOL_SPLIT
+
+
 def test_fused_residual_block_cta_pair_variant_in_a_subprocess():
     """O4D_CHAIN_PAIR=1 selects the cta_group::2 instantiation of the fused multi-layer kernel (different packed-weight
     format, cluster launch); the switch is read once per process, so the same parity test runs in a child process."""

@@ -54,6 +54,14 @@ __device__ __forceinline__ int ld_acquire_shared(uint32_t addr) {
     asm volatile("ld.acquire.cta.shared::cta.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
     return v;
 }
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {      // no wait: pair with tmem_ld_wait()
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 // byte offset of element (tile-row trow, column gc) inside an image with `cpt` chunks per tile (hi half)
@@ -230,6 +238,8 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const Program P) 
                         // written from the same mapping: 4 columns = half a core-matrix line, 8 consecutive rows = 128 B.
                         uint8_t* img_rows = op.img ? op.img + (size_t)tile * op.img_cpt * IMG_CHUNK_BYTES + (quarter * 4) * 128 + rr * 16
                                                    : nullptr;      // + it * 128: row quarter*32 + it*8 + rr
+                        uint32_t vn[16];                                 // accumulator block in flight (tcgen05.ld issued, not awaited)
+                        if (c_begin < c_end) tmem_ld16_issue(taddr + (uint32_t)c_begin, vn);
                         for (int c0 = c_begin; c0 < c_end; c0 += 16) {
                             const int gc = col_base + c0 + c4;
                             const bool col_ok = gc < op.n;
@@ -237,11 +247,13 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_chain_kernel(const Program P) 
 #pragma unroll
                             for (int it = 0; it < 4; ++it) res[it] = resn[it];
                             load_res(c0 + 16);                          // next block's residual rows: in flight during this block
-                            float v[16];
-                            tmem_ld16(taddr + (uint32_t)c0, v);
+                            tmem_ld_wait();
 #pragma unroll
                             for (int i = 0; i < 16; i += 4)
-                                *reinterpret_cast<float4*>(stg + lane * SLD + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                                *reinterpret_cast<float4*>(stg + lane * SLD + i) =
+                                    make_float4(__uint_as_float(vn[i]), __uint_as_float(vn[i + 1]), __uint_as_float(vn[i + 2]), __uint_as_float(vn[i + 3]));
+                            // the next block's accumulator columns travel while this block is transposed and written out
+                            if (c0 + 16 < c_end) tmem_ld16_issue(taddr + (uint32_t)(c0 + 16), vn);
                             __syncwarp();
                             if (col_ok) {
                                 const float4 bv = op.bias ? *reinterpret_cast<const float4*>(op.bias + gc) : make_float4(0.f, 0.f, 0.f, 0.f);

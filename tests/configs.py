@@ -107,5 +107,5 @@ def build_modules(cfg, device='cpu'):
 
 
 def weight_checksum(module):
-    return np.array([float(sum(p.double().sum() for p in module.parameters())),
-                     float(sum(p.double().abs().sum() for p in module.parameters()))])
+    return np.array([float(sum(p.detach().double().sum() for p in module.parameters())),
+                     float(sum(p.detach().double().abs().sum() for p in module.parameters()))])

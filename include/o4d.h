@@ -257,6 +257,14 @@ int o4d_decoder_prepare_scene(const o4d_decoder_config* cfg, const float* const*
                               const float* pcl_abstract, int64_t m, int64_t ld_abstract,
                               const float* feat_global,
                               void* scene, size_t scene_bytes, void* stream);
+/* Next scene, same weights: o4d_decoder_prepare_scene also builds everything that depends on the weights only
+ * (composite Qa weights, Wc, the K-concatenated lin_z folds, every packed tensor-core image).  When `scene` was prepared
+ * before with the SAME cfg, params (unchanged values) and m, this entry rewrites only the scene-dependent parts (abstract
+ * coordinates / features, K / V / Ka tables, the global half of lin_z) -- the per-frame call of a video
+ * (eval/inference.py:195-212 runs the encoder once per frame and track). */
+int o4d_decoder_update_scene(const o4d_decoder_config* cfg, const float* const* params,
+                             const float* pcl_abstract, int64_t m, int64_t ld_abstract,
+                             const float* feat_global, void* scene, size_t scene_bytes, void* stream);
 size_t o4d_decoder_workspace_bytes(const o4d_decoder_config* cfg, int64_t nq, int64_t m);
 /* query (nq, 4) -> out (nq, d_out), penult (nq, d_hidden) or NULL. */
 int o4d_decoder_forward(const o4d_decoder_config* cfg, const float* const* params,

@@ -107,7 +107,7 @@ size_t attn_tables_bytes(int64_t m, int d) {
 }
 
 int attn_tables_launch(const PtBlockParams& P, const float* ktab, const float* vtab, int64_t m, int d, void* buf,
-                       size_t buf_bytes, AttnTables* out, cudaStream_t st) {
+                       size_t buf_bytes, AttnTables* out, cudaStream_t st, bool weights_too) {
     Arena a(buf, buf_bytes);
     float* ka = a.get<float>((size_t)m * 2 * d);
     float* wc = a.get<float>((size_t)2 * d * POS_HID);
@@ -116,7 +116,7 @@ int attn_tables_launch(const PtBlockParams& P, const float* ktab, const float* v
         set_error("attention tables: buffer too small (%zu < %zu)", buf_bytes, a.off);
         return O4D_E_WORKSPACE;
     }
-    {
+    if (weights_too) {     // Wc, cvec depend on the weights only; Ka (below) on the key cloud
         ProfScope prof(PROF_MISC, 2.0 * 2 * d * d * (POS_HID + 1), st);
         matmul_nn_kernel<<<(unsigned)cdiv(2 * d * POS_HID, 256), 256, 0, st>>>(P.wa1, d, P.wp2, POS_HID, nullptr, wc, 2 * d, d, POS_HID);
         O4D_LAUNCH_CHECK();

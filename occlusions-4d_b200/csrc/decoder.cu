@@ -176,8 +176,12 @@ static void packed_set(const o4d_decoder_config* c, const DecParams& d, const Sc
     ps->pair = dec_chain_possible(c) && mlp_chain_pair();
 }
 
+// weights_too = false (o4d_decoder_update_scene): `scene` already holds everything that depends on the weights only --
+// composite Qa weights, Wc / cvec, the K-concatenated [W_pred | W_z,local] matrices, every packed tensor-core image --
+// from an earlier prepare with the same configuration, parameters and m; only the scene-dependent parts are rewritten.
 int decoder_prepare(const o4d_decoder_config* c, const float* const* P, const float* pcl_abstract, int64_t m,
-                    int64_t ld, const float* feat_global, void* scene, size_t scene_bytes, cudaStream_t st) {
+                    int64_t ld, const float* feat_global, void* scene, size_t scene_bytes, cudaStream_t st,
+                    bool weights_too = true) {
     O4D_REQUIRE(dec_cfg_ok(c), "decoder: invalid configuration");
     O4D_REQUIRE(P && pcl_abstract && feat_global && scene, "decoder prepare: null pointer");
     const int E = c->d_latent_local, H = c->d_hidden, Dg = c->d_latent - c->d_latent_local;
@@ -202,13 +206,22 @@ int decoder_prepare(const o4d_decoder_config* c, const float* const* P, const fl
         O4D_TRY(linear_launch(s.abs_feat, m, E, E, pp.wk, nullptr, H, nullptr, 0, s.ktab[j], H, 0, 0, st));
         O4D_TRY(linear_launch(s.abs_feat, m, E, E, pp.wv, nullptr, H, nullptr, 0, s.vtab[j], H, 0, 0, st));
         AttnTables T;
-        O4D_TRY(attn_tables_launch(pp, s.ktab[j], s.vtab[j], m, H, s.tables[j], s.tables_bytes, &T, st));
+        O4D_TRY(attn_tables_launch(pp, s.ktab[j], s.vtab[j], m, H, s.tables[j], s.tables_bytes, &T, st, weights_too));
+        if (!weights_too) continue;
         if (s.fused[j]) O4D_TRY(attn_fused_pack_launch(T.wc, pp.wa2, pp.wp2, H, s.fused[j], st));
         // composite input weight of the attention block (fp64 accumulation, rounded once)
         O4D_TRY(matmul_nn_launch(pp.wq, H, pp.w1, H, nullptr, s.t1[j], H, H, H, st));
         O4D_TRY(matmul_nn_launch(pp.wa1, H, s.t1[j], H, nullptr, s.wqa[j], 2 * H, H, H, st));
         O4D_TRY(matmul_nn_launch(pp.wq, H, pp.b1, 1, nullptr, s.t1b[j], H, H, 1, st));
         O4D_TRY(matmul_nn_launch(pp.wa1, H, s.t1b[j], 1, T.cvec, s.bqa[j], 2 * H, H, 1, st));
+    }
+    if (c->precision != 0 && !weights_too) {
+        // only b_pred + zg changes with the scene (zg = W_z[:, :Dg] g + b_z)
+        for (int b = 0; b < c->n_blocks; ++b) {
+            const float* bpred = b == 0 ? d.lin_in_b : (d.use_pt[b - 1] >= 0 ? d.pt[d.use_pt[b - 1]][14] : d.fc1_b[b - 1]);
+            O4D_TRY(vec_add_launch(bpred, s.zg + (size_t)b * H, s.bcat[b], H, st));
+        }
+        return 0;
     }
     if (c->precision != 0) {
         // [W_pred | pad | W_z,local] and b_pred + zg for every block (see SceneView)
@@ -527,6 +540,13 @@ extern "C" int o4d_decoder_prepare_scene(const o4d_decoder_config* cfg, const fl
                                          const float* feat_global, void* scene, size_t scene_bytes, void* stream) {
     return o4d::decoder_prepare(cfg, params, pcl_abstract, m, ld_abstract, feat_global, scene, scene_bytes,
                                 (cudaStream_t)stream);
+}
+
+extern "C" int o4d_decoder_update_scene(const o4d_decoder_config* cfg, const float* const* params,
+                                        const float* pcl_abstract, int64_t m, int64_t ld_abstract,
+                                        const float* feat_global, void* scene, size_t scene_bytes, void* stream) {
+    return o4d::decoder_prepare(cfg, params, pcl_abstract, m, ld_abstract, feat_global, scene, scene_bytes,
+                                (cudaStream_t)stream, false);
 }
 
 extern "C" size_t o4d_decoder_workspace_bytes(const o4d_decoder_config* c, int64_t nq, int64_t m) {

@@ -88,11 +88,13 @@ fps_kernel(const float* __restrict__ xyz, int n, int64_t ld, int n_out, int star
                 bi = tid + p * FPS_THREADS;
             }
         }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            float ov = __shfl_xor_sync(0xffffffffu, bv, off);
-            int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-            argmax_combine(bv, bi, ov, oi);
+        // warp arg-max in two REDUX instructions (running-min distances are >= 0, padding -1: their bit patterns order like
+        // signed integers; ties resolve to the lowest index)
+        {
+            const int vb = __float_as_int(bv);
+            const int vmax = __reduce_max_sync(0xffffffffu, vb);
+            bi = __reduce_min_sync(0xffffffffu, vb == vmax ? bi : 0x7fffffff);
+            bv = __int_as_float(vmax);
         }
         if (lane == 0) {
             s_val[warp] = bv;
@@ -102,11 +104,11 @@ fps_kernel(const float* __restrict__ xyz, int n, int64_t ld, int n_out, int star
         if (warp == 0) {
             float v = s_val[lane];
             int i = s_idx[lane];
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                float ov = __shfl_xor_sync(0xffffffffu, v, off);
-                int oi = __shfl_xor_sync(0xffffffffu, i, off);
-                argmax_combine(v, i, ov, oi);
+            {
+                const int vb = __float_as_int(v);
+                const int vmax = __reduce_max_sync(0xffffffffu, vb);
+                i = __reduce_min_sync(0xffffffffu, vb == vmax ? i : 0x7fffffff);
+                v = __int_as_float(vmax);
             }
             if (lane == 0) {
                 s_cur = i;
@@ -181,22 +183,24 @@ fps_big_kernel(const float* __restrict__ xyz, int n, int64_t ld, int n_out, int 
             mind[j] = mm;
             if (mm > bv) { bv = mm; bi = j; }
         }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            float ov = __shfl_xor_sync(0xffffffffu, bv, off);
-            int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-            argmax_combine(bv, bi, ov, oi);
+        // warp arg-max in two REDUX instructions (running-min distances are >= 0, padding -1: their bit patterns order like
+        // signed integers; ties resolve to the lowest index)
+        {
+            const int vb = __float_as_int(bv);
+            const int vmax = __reduce_max_sync(0xffffffffu, vb);
+            bi = __reduce_min_sync(0xffffffffu, vb == vmax ? bi : 0x7fffffff);
+            bv = __int_as_float(vmax);
         }
         if (lane == 0) { s_val[warp] = bv; s_idx[warp] = bi; }
         __syncthreads();
         if (warp == 0) {
             float v = s_val[lane];
             int i = s_idx[lane];
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                float ov = __shfl_xor_sync(0xffffffffu, v, off);
-                int oi = __shfl_xor_sync(0xffffffffu, i, off);
-                argmax_combine(v, i, ov, oi);
+            {
+                const int vb = __float_as_int(v);
+                const int vmax = __reduce_max_sync(0xffffffffu, vb);
+                i = __reduce_min_sync(0xffffffffu, vb == vmax ? i : 0x7fffffff);
+                v = __int_as_float(vmax);
             }
             if (lane == 0) s_cur = i;
         }

@@ -133,11 +133,13 @@ fps_cluster_kernel(const float* __restrict__ xyz, int n, int64_t ld, int n_out, 
                 bi = p * STRIDE + (int)rank * THREADS + tid;
             }
         }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-            argmax_combine(bv, bi, ov, oi);
+        // warp arg-max in two REDUX instructions instead of five shuffle / compare rounds: running-min distances are >= 0
+        // (padding -1), so their bit patterns order like signed integers; ties resolve to the lowest index
+        {
+            const int vb = __float_as_int(bv);
+            const int vmax = __reduce_max_sync(0xffffffffu, vb);
+            bi = __reduce_min_sync(0xffffffffu, vb == vmax ? bi : 0x7fffffff);
+            bv = __int_as_float(vmax);
         }
         const int par = it & 1;
         if (lane == 0) {
@@ -146,16 +148,14 @@ fps_cluster_kernel(const float* __restrict__ xyz, int n, int64_t ld, int n_out, 
         }
         __syncthreads();
         if (warp == 0) {
-            float v = lane < WARPS ? s_val[lane] : -2.f;
+            float v = lane < WARPS ? s_val[lane] : -1.f;      // (-1: the padding value, orders below every real distance)
             int i = lane < WARPS ? s_idx[lane] : 0x7fffffff;
-#pragma unroll
-            for (int off = 8; off > 0; off >>= 1) {
-                const float ov = __shfl_xor_sync(0xffffffffu, v, off);
-                const int oi = __shfl_xor_sync(0xffffffffu, i, off);
-                argmax_combine(v, i, ov, oi);
+            {
+                const int vb = __float_as_int(v);
+                const int vmax = __reduce_max_sync(0xffffffffu, vb);
+                i = __reduce_min_sync(0xffffffffu, vb == vmax ? i : 0x7fffffff);
+                v = __int_as_float(vmax);
             }
-            v = __shfl_sync(0xffffffffu, v, 0);
-            i = __shfl_sync(0xffffffffu, i, 0);
             // (a CTA without points publishes value -1 and the sentinel index: masked, so that it cannot spill into the tag)
             const uint32_t tagged = POLL ? ((((uint32_t)it + 1u) & TAG_MASK) << IDX_BITS) | ((uint32_t)i & IDX_MASK) : (uint32_t)i;
             if (lane < CTAS) st_remote_u64_addr(r_cand[par], ((uint64_t)__float_as_uint(v) << 32) | tagged);

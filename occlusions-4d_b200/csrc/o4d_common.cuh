@@ -209,7 +209,7 @@ int attn_fused_launch(const PtBlockParams& P, const AttnTables& T, const float* 
                       int precision, cudaStream_t st);
 size_t attn_tables_bytes(int64_t m, int d);
 int attn_tables_launch(const PtBlockParams& P, const float* ktab, const float* vtab, int64_t m, int d, void* buf,
-                       size_t buf_bytes, AttnTables* out, cudaStream_t st);
+                       size_t buf_bytes, AttnTables* out, cudaStream_t st, bool weights_too = true);
 int matmul_nn_launch(const float* A, int lda, const float* B, int ldb, const float* addvec, float* C, int p, int q, int r,
                      cudaStream_t st);
 size_t attn_core_workspace_bytes(int64_t n, int d, int k);

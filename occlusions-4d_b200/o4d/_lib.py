@@ -70,6 +70,8 @@ SIGNATURES = {
     'o4d_decoder_scene_bytes': (c_size, [ctypes.POINTER(DecoderConfig), c_i64]),
     'o4d_decoder_prepare_scene': (c_int, [ctypes.POINTER(DecoderConfig), c_ptr, c_ptr, c_i64, c_i64, c_ptr,
                                           c_ptr, c_size, c_ptr]),
+    'o4d_decoder_update_scene': (c_int, [ctypes.POINTER(DecoderConfig), c_ptr, c_ptr, c_i64, c_i64, c_ptr,
+                                          c_ptr, c_size, c_ptr]),
     'o4d_decoder_workspace_bytes': (c_size, [ctypes.POINTER(DecoderConfig), c_i64, c_i64]),
     'o4d_decoder_forward': (c_int, [ctypes.POINTER(DecoderConfig), c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_ptr,
                                     c_ptr, c_ptr, c_size, c_ptr]),

@@ -203,13 +203,19 @@ class LocalPclResnetFC(ResnetFC):
 
     def o4d_scene(self, pcl_abstract, features_global):
         """Scene-constant state, rebuilt when the abstract cloud, the global embedding or any
-        parameter changed (tensor identity + version counters)."""
+        parameter changed (tensor identity + version counters).  When only the scene changed -- the next frame of a
+        video, same weights, same abstract-cloud size -- the buffer is updated in place: everything that depends on the
+        weights alone (composite Qa weights, packed tensor-core images, ...) is kept."""
         params = self.o4d_params()
+        wkey = (tuple((p.data_ptr(), p._version) for p in params), self.o4d_precision, pcl_abstract.shape[0],
+                pcl_abstract.device)
         key = (pcl_abstract.data_ptr(), pcl_abstract._version, tuple(pcl_abstract.shape),
-               features_global.data_ptr(), features_global._version,
-               tuple((p.data_ptr(), p._version) for p in params), self.o4d_precision)
+               features_global.data_ptr(), features_global._version, wkey)
         if self._o4d_scene is None or key != self._o4d_scene_key:
-            self._o4d_scene = ops.DecoderScene(self.o4d_config(), params, pcl_abstract, features_global)
+            if self._o4d_scene is not None and self._o4d_scene_key[-1] == wkey:
+                self._o4d_scene.update(params, pcl_abstract, features_global)
+            else:
+                self._o4d_scene = ops.DecoderScene(self.o4d_config(), params, pcl_abstract, features_global)
             self._o4d_scene_key = key
             # strong references: while cached, the allocator cannot hand the same addresses to a
             # different scene's tensors (which would make the identity key stale).

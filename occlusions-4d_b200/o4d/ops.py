@@ -308,7 +308,7 @@ def encoder_forward(cfg, params, pcl, start_idx=None, return_levels=False):
 
 
 class DecoderScene:
-    """Scene-constant decoder state (K/V tables, lin_z global halves) living in one device buffer."""
+    """Scene-constant decoder state (K/V tables, lin_z global halves, packed weights) living in one device buffer."""
 
     def __init__(self, cfg, params, pcl_abstract, feat_global):
         L = _lib.lib()
@@ -326,6 +326,20 @@ class DecoderScene:
             rc = L.o4d_decoder_prepare_scene(ctypes.byref(cfg), tab, _ptr(a), self.m, ld, _ptr(g),
                                              _ptr(self.buf), nbytes, _stream(a))
         _lib.check(rc, 'o4d_decoder_prepare_scene')
+        del keep
+
+    def update(self, params, pcl_abstract, feat_global):
+        """Next scene with the SAME weights and abstract-cloud size: only the scene-dependent parts of the buffer are
+        rewritten (o4d_decoder_update_scene); the caller guarantees that no parameter changed since __init__."""
+        L = _lib.lib()
+        a, ld = _rows(pcl_abstract, 'pcl_abstract')
+        g = _f32(feat_global, 'features_global').contiguous().reshape(-1)
+        assert a.shape[0] == self.m and a.shape[1] == 3 + self.cfg.d_latent_local and a.device == self.buf.device
+        tab, keep = param_table(params)
+        with torch.cuda.device(a.device):
+            rc = L.o4d_decoder_update_scene(ctypes.byref(self.cfg), tab, _ptr(a), self.m, ld, _ptr(g),
+                                            _ptr(self.buf), self.buf.numel(), _stream(a))
+        _lib.check(rc, 'o4d_decoder_update_scene')
         del keep
 
 

@@ -106,6 +106,36 @@ def test_call_forms_of_both_reference_callers():
             dec(q[None].expand(2, -1, -1), r3[0].expand(2, -1, -1), r3[1].expand(2, -1), None)  # B must be 1
 
 
+def test_next_scene_updates_the_scene_buffer_in_place():
+    """A second scene with the same weights and abstract-cloud size takes o4d_decoder_update_scene (the weight-only parts
+    of the scene buffer are reused); results must equal a freshly prepared scene bit for bit, and a parameter change
+    must force a full prepare."""
+    g = load('c1_greater_seeded.npz')
+    cfg = configs.C1_GREATER
+    _, dec = modules_from_golden(cfg, g)
+    _, fresh = modules_from_golden(cfg, g)
+    q = g['query'].to(DEV)
+    a1, g1 = g['abstract'].to(DEV), g['glob'].to(DEV)
+    gen = torch.Generator().manual_seed(3)
+    a2 = torch.cat([a1[:, :3].cpu() + 0.25 * torch.randn(a1.shape[0], 3, generator=gen),
+                    a1[:, 3:].cpu() * 1.5], dim=1).to(DEV)
+    g2 = (g1.cpu() + torch.randn(g1.shape, generator=gen)).to(DEV)
+    with torch.no_grad():
+        o1, _ = dec(q, a1, g1, None)
+        scene1 = dec._o4d_scene
+        o2, _ = dec(q, a2, g2, None)                       # same weights, same m -> in-place update
+        assert dec._o4d_scene is scene1
+        want2, _ = fresh(q, a2, g2, None)                  # fresh module: full prepare on scene 2
+        assert torch.equal(o2, want2)
+        assert relerr(o1.cpu(), g['out']) < TOL_TIGHT
+        o1b, _ = dec(q, a1, g1, None)                      # and back
+        assert torch.equal(o1b, o1)
+        dec.lin_out.bias.add_(1.0)                         # parameter version bump -> full prepare, new buffer contents
+        o3, _ = dec(q, a1, g1, None)
+        assert dec._o4d_scene is not scene1
+        assert relerr((o3 - 1.0).cpu(), o1.cpu()) < 1e-6
+
+
 def test_batched_encoder_equals_per_cloud():
     g = load('tiny_greater.npz')
     enc, _ = modules_from_golden(configs.TINY_GREATER, g)

@@ -77,6 +77,20 @@ int o4d_knn_f32(const float* query, int64_t nq, int64_t ldq,
                 int k, int sqrt_dist,
                 int64_t* idx_out, float* dist_out, void* stream);
 
+/* Both neighbour lists of the decoder from ONE scan of the reference cloud (same query, same cloud):
+ *   idx_out  (nq, k)  the k nearest by SQUARED distance, ascending (d2, index)   -- kNN_torch, point_transformer_layer.py:76-99
+ *   idx2_out (nq, k2), dist2_out (nq, k2)  the k2 < k nearest by EUCLIDEAN distance, ascending (sqrt(d2), index), with
+ *            their distances                                                      -- my_knn_torch, utils/geometry.py:458-503
+ * Results are identical to two o4d_knn_f32 calls (sqrt_dist 0 / 1), including the index tie-break where two different
+ * squared distances round to the same root.  Requires 9 <= k <= O4D_MAX_K, k2 < k <= m.
+ * workspace: o4d_knn_two_lists_workspace_bytes(nq, k, k2). */
+size_t o4d_knn_two_lists_workspace_bytes(int64_t nq, int k, int k2);
+int o4d_knn_two_lists_f32(const float* query, int64_t nq, int64_t ldq,
+                          const float* ref, int64_t m, int64_t ldr,
+                          int k, int k2,
+                          int64_t* idx_out, int64_t* idx2_out, float* dist2_out,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------ FPS
  * Farthest point sampling of one cloud, replaces torch_cluster.fps + torch.sort at
  * model/modules.py:133-135.  Start point = start_idx (0 = deterministic, the

@@ -371,7 +371,11 @@ static int decoder_forward_chain(const o4d_decoder_config* c, const DecParams& d
                                  const DecWs& w, int64_t m, const float* query, const float* in_ptr, int in_w, int64_t nq,
                                  float* out, float* penult, cudaStream_t st) {
     const int H = c->d_hidden, E = c->d_latent_local;
-    O4D_TRY(act_image_launch(in_ptr, in_w, nq, in_w, 0, w.img_pe, st));
+    // implicit.py:403-406: the Fourier features, written straight into the image lin_in reads
+    if (c->pos_encoding_freqs > 0)
+        O4D_TRY(posenc_image_launch(query, nq, c->d_in, c->pos_encoding_freqs, w.img_pe, st));
+    else
+        O4D_TRY(act_image_launch(in_ptr, in_w, nq, in_w, 0, w.img_pe, st));
     // w.img_floc: written by the local-feature blend itself (decoder_forward)
     float* qa = (float*)w.sub;                        // (nq, 2H): first carve of the attention workspace
     ChainBuild cb(nq, c->precision == 1 ? 1 : 0, st);
@@ -445,14 +449,21 @@ int decoder_forward(const o4d_decoder_config* c, const float* const* P, const vo
     PackedSet ps;
     packed_set(c, d, s, m, scene, &ps);
 
-    // implicit.py:328-339  K_l nearest abstract points, inverse-distance blend of their features
-    O4D_TRY(knn_launch(query, nq, c->d_in, s.abs_xyz, m, 3, c->num_local_features, 1, w.idx_l, nullptr, w.dist_l, st));
+    // implicit.py:328-339  K_l nearest abstract points, inverse-distance blend of their features.
+    // point_transformer_layer.py:167  K_c nearest abstract points -- identical for every cross layer (same query / abstract
+    // cloud).  Both lists come from ONE scan of the abstract cloud when K_l < K_c (the released configurations: 8 / 14).
+    const bool one_scan = c->cross_attn_layers > 0 && c->cross_attn_neighbors >= 9 && c->num_local_features < c->cross_attn_neighbors;
+    if (one_scan)
+        O4D_TRY(knn_dual_launch(query, nq, c->d_in, s.abs_xyz, m, 3, c->cross_attn_neighbors, w.idx_c, c->num_local_features,
+                                w.idx_l, w.dist_l, st));
+    else
+        O4D_TRY(knn_launch(query, nq, c->d_in, s.abs_xyz, m, 3, c->num_local_features, 1, w.idx_l, nullptr, w.dist_l, st));
     // (fused multi-layer path: straight into the activation image lin_z's layers read; no fp32 copy is needed)
     const bool chain = w.img_x != nullptr && nq >= 1024;
     O4D_TRY(local_blend_launch(w.idx_l, w.dist_l, s.abs_feat, E, nq, c->num_local_features, E, w.f_loc, E, st,
                                chain ? w.img_floc : nullptr));
     // point_transformer_layer.py:167 -- identical for every cross layer (same query / abstract cloud)
-    if (c->cross_attn_layers > 0)
+    if (c->cross_attn_layers > 0 && !one_scan)
         O4D_TRY(knn_launch(query, nq, c->d_in, s.abs_xyz, m, 3, c->cross_attn_neighbors, 0, w.idx_c, nullptr, nullptr, st));
     // lin_z folded into the producing layer whenever the packed K-concatenated weights exist
     const bool fold = prec != 0 && ps.find(s.wcat[0]) != nullptr && tc_shape_ok(nq, H, H) &&
@@ -464,7 +475,7 @@ int decoder_forward(const o4d_decoder_config* c, const float* const* P, const vo
     // implicit.py:403-408 (+ :416-418 of block 0 when folded)
     const float* in_ptr = c->pos_encoding_freqs > 0 ? w.pe : query;
     const int in_w = c->pos_encoding_freqs > 0 ? pe_w : c->d_in;
-    if (c->pos_encoding_freqs > 0) O4D_TRY(posenc_launch(query, nq, c->d_in, c->pos_encoding_freqs, w.pe, st));
+    if (c->pos_encoding_freqs > 0 && !chain) O4D_TRY(posenc_launch(query, nq, c->d_in, c->pos_encoding_freqs, w.pe, st));
     if (chain) {
         if (!fold) {
             set_error("decoder: fused MLP path selected but the folded weights are missing");

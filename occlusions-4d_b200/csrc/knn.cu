@@ -56,11 +56,22 @@ struct TopK {
     }
 };
 
+// Second result of the same scan (decoder: the K_l = 8 Euclidean neighbours of implicit.py:328 next to the K_c = 14
+// squared-distance neighbours of point_transformer_layer.py:167, same query, same cloud): the k2 nearest under the key
+// (sqrt(d2) correctly rounded, index).  sqrt is monotone, so they are among the k nearest under (d2, index) unless the
+// rounded roots of the k2-th and the k-th coincide; inside the list only runs of equal roots need re-ordering by index
+// (two different d2 can round to the same root).  Both rare cases are handled exactly (run fix-up, rescan).
+struct KnnSecond {
+    int k2 = 0;
+    int32_t* idx32 = nullptr;     // (nq, k2)
+    float* dist = nullptr;        // (nq, k2) Euclidean distances
+};
+
 template <int KMAX, int S, bool SQRT>
 __global__ void __launch_bounds__(KNN_THREADS)
 knn_kernel(const float* __restrict__ query, int64_t nq, int64_t ldq,
            const float* __restrict__ ref, int m, int64_t ldr, int k,
-           int32_t* __restrict__ idx32, int64_t* __restrict__ idx64, float* __restrict__ dist_out) {
+           int32_t* __restrict__ idx32, int64_t* __restrict__ idx64, float* __restrict__ dist_out, KnnSecond second) {
     __shared__ float sx[KNN_TILE], sy[KNN_TILE], sz[KNN_TILE];
     constexpr int QPB = KNN_THREADS / S;  // queries per block
     const int sub = threadIdx.x % S;
@@ -97,7 +108,13 @@ knn_kernel(const float* __restrict__ query, int64_t nq, int64_t ldq,
 
     // merge the S sub-lane lists: k rounds of "global minimum of the heads".
     const unsigned full = 0xffffffffu;
-    for (int r = 0; r < k; ++r) {
+    float md[KMAX];
+    int mi[KMAX];
+#pragma unroll
+    for (int t = 0; t < KMAX; ++t) { md[t] = CUDART_INF_F; mi[t] = 0x7fffffff; }
+#pragma unroll
+    for (int r = 0; r < KMAX; ++r) {
+        if (r >= k) break;
         float bd = top.d[0];
         int bi = top.i[0];
         if (S > 1) {
@@ -114,24 +131,64 @@ knn_kernel(const float* __restrict__ query, int64_t nq, int64_t ldq,
         } else {
             top.pop_front();
         }
+        md[r] = bd;
+        mi[r] = bi;
         if (live && sub == 0) {
             if (idx32) idx32[qi * k + r] = bi;
             if (idx64) idx64[qi * k + r] = (int64_t)bi;
             if (dist_out) dist_out[qi * k + r] = bd;
         }
     }
+    if (!SQRT && second.k2 > 0 && live && sub == 0) {
+        const int k2 = second.k2;
+        float sr[KMAX];
+#pragma unroll
+        for (int t = 0; t < KMAX; ++t) sr[t] = t < k ? __fsqrt_rn(md[t]) : CUDART_INF_F;
+        if (sr[k2 - 1] == sr[k - 1]) {
+            // a point outside the list may tie with the k2-th root: exact rescan under the (root, index) key
+            TopK<KMAX> t2;
+            t2.init();
+            for (int j = 0; j < m; ++j) {
+                const float* r = ref + (int64_t)j * ldr;
+                const float dx = qx - r[0], dy = qy - r[1], dz = qz - r[2];
+                t2.push(__fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz))), j);
+            }
+#pragma unroll
+            for (int t = 0; t < KMAX; ++t) { sr[t] = t2.d[t]; mi[t] = t2.i[t]; }
+        } else {
+            // inside the list: equal roots in ascending index (the list is ordered by (d2, index))
+            bool dirty = false;
+#pragma unroll
+            for (int t = 0; t + 1 < KMAX; ++t) dirty = dirty || (t + 1 < k && sr[t] == sr[t + 1] && mi[t] > mi[t + 1]);
+            while (dirty) {
+                dirty = false;
+#pragma unroll
+                for (int t = 0; t + 1 < KMAX; ++t)
+                    if (t + 1 < k && sr[t] == sr[t + 1] && mi[t] > mi[t + 1]) {
+                        const int ti = mi[t]; mi[t] = mi[t + 1]; mi[t + 1] = ti;
+                        dirty = true;
+                    }
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < KMAX; ++t)
+            if (t < k2) {
+                if (second.idx32) second.idx32[qi * k2 + t] = mi[t];
+                if (second.dist) second.dist[qi * k2 + t] = sr[t];
+            }
+    }
 }
 
 template <int KMAX, bool SQRT>
 static int knn_dispatch_s(int S, dim3 grid_unused, const float* query, int64_t nq, int64_t ldq,
                           const float* ref, int m, int64_t ldr, int k, int32_t* idx32,
-                          int64_t* idx64, float* dist, cudaStream_t st) {
+                          int64_t* idx64, float* dist, cudaStream_t st, KnnSecond second = KnnSecond()) {
     (void)grid_unused;
 #define O4D_KNN_CASE(SV)                                                                         \
     case SV: {                                                                                   \
         int64_t blocks = cdiv(nq, KNN_THREADS / SV);                                             \
         knn_kernel<KMAX, SV, SQRT><<<(unsigned)blocks, KNN_THREADS, 0, st>>>(                    \
-            query, nq, ldq, ref, m, ldr, k, idx32, idx64, dist);                                 \
+            query, nq, ldq, ref, m, ldr, k, idx32, idx64, dist, second);                         \
         break;                                                                                   \
     }
     switch (S) {
@@ -145,6 +202,27 @@ static int knn_dispatch_s(int S, dim3 grid_unused, const float* query, int64_t n
 #undef O4D_KNN_CASE
     O4D_LAUNCH_CHECK();
     return 0;
+}
+
+// One scan, two neighbour lists: the k nearest by squared distance (idx32) and the k2 <= k nearest by Euclidean distance
+// with their distances (idx2, dist2); see KnnSecond.
+int knn_dual_launch(const float* query, int64_t nq, int64_t ldq, const float* ref, int64_t m, int64_t ldr, int k,
+                    int32_t* idx32, int k2, int32_t* idx2, float* dist2, cudaStream_t st) {
+    // k2 < k: the k-th root bounds every point outside the list, which is what makes the in-list selection exact
+    O4D_REQUIRE(k >= 9 && k <= O4D_MAX_K && k2 >= 1 && k2 < k && m >= k && m < (int64_t)0x7fffffff,
+                "knn (two lists): need 1 <= k2 < k, 9 <= k <= %d <= m", O4D_MAX_K);
+    if (nq == 0) return 0;
+    O4D_REQUIRE(query && ref && idx32 && idx2 && dist2 && ldq >= 3 && ldr >= 3, "knn (two lists): bad argument");
+    ProfScope prof(PROF_KNN, 8.0 * (double)nq * (double)m, st);
+    int S = 1;
+    if (nq * 1 < 600000 && m >= 128) S = 4;
+    if (nq * 4 < 600000 && m >= 1024) S = 32;
+    KnnSecond second;
+    second.k2 = k2;
+    second.idx32 = idx2;
+    second.dist = dist2;
+    dim3 g;
+    return knn_dispatch_s<16, false>(S, g, query, nq, ldq, ref, (int)m, ldr, k, idx32, nullptr, nullptr, st, second);
 }
 
 int knn_launch(const float* query, int64_t nq, int64_t ldq, const float* ref, int64_t m,
@@ -184,4 +262,28 @@ extern "C" int o4d_knn_f32(const float* query, int64_t nq, int64_t ldq, const fl
     O4D_REQUIRE(nq == 0 || idx_out || dist_out, "o4d_knn_f32: no output requested");
     return o4d::knn_launch(query, nq, ldq, ref, m, ldr, k, sqrt_dist, nullptr, idx_out, dist_out,
                            (cudaStream_t)stream);
+}
+
+extern "C" size_t o4d_knn_two_lists_workspace_bytes(int64_t nq, int k, int k2) {
+    if (nq < 0 || k < 1 || k2 < 1) return 0;
+    return o4d::align_up((size_t)nq * k * sizeof(int32_t), 256) + o4d::align_up((size_t)nq * k2 * sizeof(int32_t), 256);
+}
+
+extern "C" int o4d_knn_two_lists_f32(const float* query, int64_t nq, int64_t ldq, const float* ref, int64_t m, int64_t ldr,
+                                     int k, int k2, int64_t* idx_out, int64_t* idx2_out, float* dist2_out, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
+    using namespace o4d;
+    O4D_REQUIRE(nq == 0 || (idx_out && idx2_out && dist2_out && workspace), "knn (two lists): null pointer");
+    if (nq == 0) return 0;
+    Arena a(workspace, workspace_bytes);
+    int32_t* i1 = a.get<int32_t>((size_t)nq * k);
+    int32_t* i2 = a.get<int32_t>((size_t)nq * k2);
+    if (!a.ok) {
+        set_error("knn (two lists): workspace too small (%zu < %zu)", workspace_bytes, a.off);
+        return O4D_E_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    O4D_TRY(knn_dual_launch(query, nq, ldq, ref, m, ldr, k, i1, k2, i2, dist2_out, st));
+    O4D_TRY(widen_idx_launch(i1, nq * k, idx_out, st));
+    return widen_idx_launch(i2, nq * k2, idx2_out, st);
 }

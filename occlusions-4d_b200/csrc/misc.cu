@@ -33,6 +33,68 @@ __global__ void posenc_kernel(const float* __restrict__ q, int64_t n, int d_in, 
     out[e] = v;
 }
 
+// The same features written straight into the activation image the fused multi-layer kernel reads (mlp_chain.cuh layout:
+// per (128-row tile, 32-column chunk) [bf16 hi 8 KB][bf16 lo 8 KB], each [k/8][row/8][8 rows][8 values]; padding rows and
+// columns zero).  Thread = (row, 8-column group): a warp's stores are 4 x 128 contiguous bytes per image half.
+__global__ void posenc_image_kernel(const float* __restrict__ q, int64_t n, int d_in, int n_freq, uint8_t* __restrict__ img,
+                                    int cpt, int64_t tiles) {
+    const int width = d_in * (2 * n_freq + 1);
+    const int64_t units = tiles * cpt * (128 * 4);
+    for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < units; u += (int64_t)gridDim.x * blockDim.x) {
+        const int kc = (int)(u & 3);
+        const int trow = (int)((u >> 2) % 128);
+        const int64_t tc = u / (128 * 4);
+        const int chunk = (int)(tc % cpt);
+        const int64_t tile = tc / cpt;
+        const int64_t i = tile * 128 + trow;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int c = chunk * 32 + kc * 8 + e;
+            float x = 0.f;
+            if (i < n && c < width) {
+                if (c < d_in) {
+                    x = q[i * d_in + c];
+                } else {
+                    const int t = c - d_in;
+                    const int p = t / (2 * d_in);
+                    const int r = t % (2 * d_in);
+                    const float omega = (float)(0.1 * (double)(1 << p) * 3.141592653589793 * 2.0);
+                    const float arg = q[i * d_in + (r % d_in)] * omega;
+                    x = (r < d_in) ? sinf(arg) : cosf(arg);
+                }
+            }
+            v[e] = x;
+        }
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+            hi[e] = *reinterpret_cast<const uint32_t*>(&h);
+            const float ha = __uint_as_float(hi[e] << 16), hb = __uint_as_float(hi[e] & 0xffff0000u);
+            const __nv_bfloat162 l = __floats2bfloat162_rn(v[2 * e] - ha, v[2 * e + 1] - hb);
+            lo[e] = *reinterpret_cast<const uint32_t*>(&l);
+        }
+        uint8_t* dst = img + ((size_t)tile * cpt + chunk) * 16384 + kc * 2048 + (trow >> 3) * 128 + (trow & 7) * 16;
+        *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(dst + 8192) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+int posenc_image_launch(const float* q, int64_t n, int d_in, int n_freq, void* img, cudaStream_t st) {
+    if (n == 0) return 0;
+    O4D_REQUIRE(n_freq >= 0 && n_freq <= 24, "posenc: bad frequency count %d", n_freq);
+    const int width = d_in * (2 * n_freq + 1);
+    const int cpt = (width + 31) / 32;
+    const int64_t tiles = cdiv(cdiv(n, 128), 2) * 2;          // image buffers cover an even number of row tiles
+    const int64_t units = tiles * cpt * (128 * 4);
+    int64_t blocks = cdiv(units, 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    posenc_image_kernel<<<(unsigned)blocks, 256, 0, st>>>(q, n, d_in, n_freq, (uint8_t*)img, cpt, tiles);
+    O4D_LAUNCH_CHECK();
+    return 0;
+}
+
 int posenc_launch(const float* q, int64_t n, int d_in, int n_freq, float* out, cudaStream_t st) {
     if (n == 0) return 0;
     O4D_REQUIRE(n_freq >= 0 && n_freq <= 24, "posenc: bad frequency count %d", n_freq);

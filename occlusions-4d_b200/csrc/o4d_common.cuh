@@ -124,6 +124,9 @@ struct RowGather {
 int knn_launch(const float* query, int64_t nq, int64_t ldq, const float* ref, int64_t m,
                int64_t ldr, int k, int sqrt_dist, int32_t* idx32, int64_t* idx64, float* dist,
                cudaStream_t st);
+// one scan -> the k nearest by squared distance and the k2 <= k nearest by Euclidean distance (+ distances)
+int knn_dual_launch(const float* query, int64_t nq, int64_t ldq, const float* ref, int64_t m, int64_t ldr, int k,
+                    int32_t* idx32, int k2, int32_t* idx2, float* dist2, cudaStream_t st);
 int fps_launch(const float* xyz, int64_t n, int64_t ld, int64_t n_out, int64_t start,
                int32_t* idx_sorted32, int64_t* idx_sorted64, int64_t* order64, void* ws,
                size_t ws_bytes, cudaStream_t st);
@@ -230,6 +233,8 @@ int down_launch(const float* const* p, const float* x, int64_t n, int d_in, cons
 
 // misc elementwise / gather kernels (misc.cu)
 int posenc_launch(const float* q, int64_t n, int d_in, int n_freq, float* out, cudaStream_t st);
+// the same features as the activation image of the fused multi-layer kernel (no fp32 copy)
+int posenc_image_launch(const float* q, int64_t n, int d_in, int n_freq, void* img, cudaStream_t st);
 // img != nullptr: the blend is written as an activation image (ceil(e / 32) chunks per 128-row tile) instead of fp32 rows
 int local_blend_launch(const int32_t* idx, const float* dist, const float* feat, int64_t ldfeat,
                        int64_t n, int k, int e, float* out, int64_t ldout, cudaStream_t st, void* img = nullptr);

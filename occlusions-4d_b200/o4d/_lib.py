@@ -41,6 +41,9 @@ SIGNATURES = {
     'o4d_profile_enable': (None, [c_int]),
     'o4d_profile_read': (c_int, [c_int, c_ptr, c_ptr, c_ptr]),
     'o4d_knn_f32': (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_i64, c_i64, c_int, c_int, c_ptr, c_ptr, c_ptr]),
+    'o4d_knn_two_lists_workspace_bytes': (c_size, [c_i64, c_int, c_int]),
+    'o4d_knn_two_lists_f32': (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_i64, c_i64, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_size,
+                                      c_ptr]),
     'o4d_fps_workspace_bytes': (c_size, [c_i64, c_i64]),
     'o4d_fps_f32': (c_int, [c_ptr, c_i64, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_size, c_ptr]),
     'o4d_linear_f32': (c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_i64,

@@ -103,6 +103,25 @@ def knn(query, ref, k, sqrt_dist=False, return_dist=False):
     return (idx, dist) if return_dist else idx
 
 
+def knn_two_lists(query, ref, k, k2):
+    """One scan of `ref`: (idx (n, k) by squared distance, idx2 (n, k2), dist2 (n, k2) by Euclidean distance); identical
+    to knn(..., k) and knn(..., k2, sqrt_dist=True, return_dist=True)."""
+    q, ldq = _rows(query, 'query')
+    r, ldr = _rows(ref, 'ref')
+    L = _lib.lib()
+    n = q.shape[0]
+    with torch.cuda.device(q.device):
+        idx = torch.empty((n, k), dtype=torch.int64, device=q.device)
+        idx2 = torch.empty((n, k2), dtype=torch.int64, device=q.device)
+        dist2 = torch.empty((n, k2), dtype=torch.float32, device=q.device)
+        nbytes = L.o4d_knn_two_lists_workspace_bytes(n, int(k), int(k2))
+        ws = workspace(q.device, nbytes, slot=5)
+        rc = L.o4d_knn_two_lists_f32(_ptr(q), n, ldq, _ptr(r), r.shape[0], ldr, int(k), int(k2), _ptr(idx), _ptr(idx2),
+                                     _ptr(dist2), _ptr(ws), ws.numel(), _stream(q))
+    _lib.check(rc, 'o4d_knn_two_lists_f32')
+    return idx, idx2, dist2
+
+
 def fps(xyz, n_out, start_idx=0, return_order=False):
     """xyz (N, >=3) -> sorted indices (n_out,) int64 [, selection order]."""
     p, ld = _rows(xyz, 'xyz')

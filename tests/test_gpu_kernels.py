@@ -75,6 +75,28 @@ def test_knn_encoder_self_shape_bit_exact():
     assert bool((oi[:, 0] == torch.arange(14336)).all())  # every point is its own nearest neighbour
 
 
+@pytest.mark.parametrize('nq,m,k,k2', [(5000, 531, 14, 8), (3000, 2124, 14, 8), (700, 300, 16, 15), (64, 20, 9, 3)])
+def test_knn_two_lists_from_one_scan_equal_two_scans(nq, m, k, k2):
+    """The decoder's two neighbour lists (squared-distance K_c, Euclidean K_l + distances) from one scan must be
+    IDENTICAL to the two separate kernels, on clouds with exact duplicates (abstract_levels = 2 duplicates every
+    level-2 position) and with many near-equal distances (points on a lattice: equal and nearly equal roots)."""
+    g = torch.Generator().manual_seed(nq + m)
+    ref = torch.rand(m, 3, generator=g) * 10 - 5
+    ref[m // 2:m // 2 + m // 4] = ref[:m // 4]                          # exact duplicates
+    ref[-(m // 5):] = torch.round(ref[-(m // 5):] * 2) / 2               # lattice points: many equal distances
+    q = torch.rand(nq, 3, generator=g) * 10 - 5
+    q[:nq // 4] = torch.round(q[:nq // 4] * 2) / 2 + 0.25
+    idx, idx2, d2 = ops.knn_two_lists(q.to(DEV), ref.to(DEV), k, k2)
+    want = ops.knn(q.to(DEV), ref.to(DEV), k)
+    want2, wantd = ops.knn(q.to(DEV), ref.to(DEV), k2, sqrt_dist=True, return_dist=True)
+    assert torch.equal(idx, want)
+    assert torch.equal(idx2, want2)
+    assert torch.equal(d2, wantd)
+    # and against the oracle's canonical rule
+    oi, od = orc.knn_indices(q, ref, k2, sqrt=True)
+    assert torch.equal(idx2.cpu(), oi) and torch.equal(d2.cpu(), od)
+
+
 def test_knn_rejects_bad_arguments():
     q = torch.rand(4, 3, device=DEV)
     with pytest.raises(RuntimeError, match='k='):

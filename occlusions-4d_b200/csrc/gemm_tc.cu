@@ -22,6 +22,7 @@
 // epilogue overlaps the other's main loop.
 #include "o4d_common.cuh"
 #include <cuda_bf16.h>
+#include "tc_helpers.cuh"
 #include <stdlib.h>
 
 namespace o4d {
@@ -286,21 +287,22 @@ linear_tc_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda, 
 #pragma unroll
             for (int g = 0; g < GPW; ++g) {
                 const int rg = warp * GPW + g;                // 8-row group inside the 128-row tile
-                __align__(16) __nv_bfloat16 h[8];
-                __align__(16) __nv_bfloat16 l[8];
+                __align__(16) uint32_t h[4];
+                __align__(16) uint32_t l[4];
                 const bool relu_c = relu_in && c < k1c;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    float x = relu_c ? fmaxf(cur[g][i], 0.f) : cur[g][i];
-                    split_bf16(x, h[i], l[i]);
+                for (int i = 0; i < 4; ++i) {   // packed conversions (full rate), see tch::split_bf16x2
+                    const float x0 = relu_c ? fmaxf(cur[g][2 * i], 0.f) : cur[g][2 * i];
+                    const float x1 = relu_c ? fmaxf(cur[g][2 * i + 1], 0.f) : cur[g][2 * i + 1];
+                    tch::split_bf16x2(x0, x1, h[i], l[i]);
                 }
                 // [kc][row group][row][16 B]: floats 4p..4p+3 are half (p & 1) of core-matrix line kc = p >> 1,
                 // floats 16+4p.. the same half of line kc + 2
                 const int off = (pq >> 1) * (BM * 16) + rg * 128 + rr * 16 + (pq & 1) * 8;
                 *reinterpret_cast<uint2*>(a_hi + off) = *reinterpret_cast<const uint2*>(h);
                 *reinterpret_cast<uint2*>(a_lo + off) = *reinterpret_cast<const uint2*>(l);
-                *reinterpret_cast<uint2*>(a_hi + off + 2 * (BM * 16)) = *reinterpret_cast<const uint2*>(h + 4);
-                *reinterpret_cast<uint2*>(a_lo + off + 2 * (BM * 16)) = *reinterpret_cast<const uint2*>(l + 4);
+                *reinterpret_cast<uint2*>(a_hi + off + 2 * (BM * 16)) = *reinterpret_cast<const uint2*>(h + 2);
+                *reinterpret_cast<uint2*>(a_lo + off + 2 * (BM * 16)) = *reinterpret_cast<const uint2*>(l + 2);
             }
             fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
             __syncwarp();

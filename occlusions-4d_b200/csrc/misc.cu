@@ -128,13 +128,48 @@ local_blend_kernel(const int32_t* __restrict__ idx, const float* __restrict__ di
         }
     }
     const float denom = fmaxf(sum, 1e-12f);
+#pragma unroll
+    for (int j = 0; j < O4D_MAX_K; ++j)
+        if (j < k) w[j] = w[j] / denom;
     const int cpt = (e + 31) / 32;
+    // four channels per lane and step (16-byte loads of the gathered rows) when the rows allow it
+    const bool vec = (e % 4 == 0) && (ldfeat % 4 == 0) && ((reinterpret_cast<uintptr_t>(feat) & 15) == 0) &&
+                     (IMG || ((ldout % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)));
+    if (vec) {
+        const int cend = IMG ? cpt * 32 : e;
+        for (int c = lane * 4; c < cend; c += 128) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c < e) {
+#pragma unroll
+                for (int j = 0; j < O4D_MAX_K; ++j) {
+                    if (j < k) {
+                        const float4 f = __ldg(reinterpret_cast<const float4*>(feat + (int64_t)id[j] * ldfeat + c));
+                        acc.x = fmaf(w[j], f.x, acc.x); acc.y = fmaf(w[j], f.y, acc.y);
+                        acc.z = fmaf(w[j], f.z, acc.z); acc.w = fmaf(w[j], f.w, acc.w);
+                    }
+                }
+            }
+            if (!IMG) {
+                *reinterpret_cast<float4*>(out + i * ldout + c) = acc;
+            } else {
+                const __nv_bfloat162 h0 = __floats2bfloat162_rn(acc.x, acc.y), h1 = __floats2bfloat162_rn(acc.z, acc.w);
+                const uint32_t u0 = *reinterpret_cast<const uint32_t*>(&h0), u1 = *reinterpret_cast<const uint32_t*>(&h1);
+                const __nv_bfloat162 l0 = __floats2bfloat162_rn(acc.x - __uint_as_float(u0 << 16), acc.y - __uint_as_float(u0 & 0xffff0000u));
+                const __nv_bfloat162 l1 = __floats2bfloat162_rn(acc.z - __uint_as_float(u1 << 16), acc.w - __uint_as_float(u1 & 0xffff0000u));
+                uint8_t* dst = img + ((size_t)(i >> 7) * cpt + (c >> 5)) * 16384 + ((c & 31) >> 3) * 2048 + (((int)i & 127) >> 3) * 128 +
+                               ((int)i & 7) * 16 + (c & 7) * 2;
+                *reinterpret_cast<uint2*>(dst) = make_uint2(u0, u1);
+                *reinterpret_cast<uint2*>(dst + 8192) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+            }
+        }
+        return;
+    }
     for (int c = lane; c < (IMG ? cpt * 32 : e); c += 32) {
         float acc = 0.f;
         if (c < e) {
 #pragma unroll
             for (int j = 0; j < O4D_MAX_K; ++j) {
-                if (j < k) acc = fmaf(w[j] / denom, feat[(int64_t)id[j] * ldfeat + c], acc);
+                if (j < k) acc = fmaf(w[j], feat[(int64_t)id[j] * ldfeat + c], acc);
             }
         }
         if (!IMG) {

@@ -17,6 +17,7 @@
 // by reduce_partials_kernel (train.cu): deterministic.
 #include "o4d_common.cuh"
 #include <cuda_bf16.h>
+#include "tc_helpers.cuh"
 
 namespace o4d {
 namespace wg {
@@ -93,16 +94,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+// Eight values of one operand column -> one 16-byte core-matrix line per image half.  Packed conversions
+// (tch::split_bf16x2: F2FP.BF16.F32.PACK_AB, full rate) -- the scalar F2F form ran on the quarter-rate conversion
+// pipe and made the producers, not the tensor pipe, the bound of this kernel (96 F2F per thread and 32-row chunk).
 __device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
-    __align__(16) __nv_bfloat16 h[8];
-    __align__(16) __nv_bfloat16 l[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        h[i] = __float2bfloat16_rn(x[i]);
-        l[i] = __float2bfloat16_rn(x[i] - __bfloat162float(h[i]));
-    }
-    hi = *reinterpret_cast<const uint4*>(h);
-    lo = *reinterpret_cast<const uint4*>(l);
+    tch::split_bf16x2(x[0], x[1], hi.x, lo.x);
+    tch::split_bf16x2(x[2], x[3], hi.y, lo.y);
+    tch::split_bf16x2(x[4], x[5], hi.z, lo.z);
+    tch::split_bf16x2(x[6], x[7], hi.w, lo.w);
 }
 
 struct Tiling {

@@ -86,7 +86,7 @@ linear_simt_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda
             if (bias) v += bias[gc];
             if (gq) v += gq[gc] - gk[gc];
             if (relu_out) v = fmaxf(v, 0.f);
-            if (R) v += R[gr * ldr + gc];
+            if (R) v = (flags & O4D_MASK_RES) ? (R[gr * ldr + gc] > 0.f ? v : 0.f) : v + R[gr * ldr + gc];
             C[gr * ldc + gc] = v;
         }
     }

@@ -324,6 +324,7 @@ linear_tc_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda, 
         tc_fence_after();
         if (dbg) g_dbg_tc[2] = clock64();
         const bool relu_out = flags & O4D_RELU_OUT;
+        const bool mask_res = flags & O4D_MASK_RES;         // R is a ReLU mask, not an addend
         const int quarter = warp & 3, chalf = warp >> 2;
         const int64_t warp_row0 = row0 + quarter * 32;
         const int col_base = tile_n * bn;
@@ -376,7 +377,12 @@ linear_tc_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda, 
                             float4 x = *reinterpret_cast<const float4*>(stg + row * SLD + c4);
                             x.x += bv.x; x.y += bv.y; x.z += bv.z; x.w += bv.w;
                             if (relu_out) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
-                            x.x += res[it].x; x.y += res[it].y; x.z += res[it].z; x.w += res[it].w;
+                            if (mask_res) {
+                                x.x = res[it].x > 0.f ? x.x : 0.f; x.y = res[it].y > 0.f ? x.y : 0.f;
+                                x.z = res[it].z > 0.f ? x.z : 0.f; x.w = res[it].w > 0.f ? x.w : 0.f;
+                            } else {
+                                x.x += res[it].x; x.y += res[it].y; x.z += res[it].z; x.w += res[it].w;
+                            }
                             *reinterpret_cast<float4*>(C + (warp_row0 + row) * ldc + gc) = x;
                         }
                     }
@@ -402,7 +408,7 @@ linear_tc_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda, 
                         float x = v[i] + (bias ? bias[gc0 + i] : 0.f);
                         if (gq) x += gq[gc0 + i] - gk[gc0 + i];
                         if (relu_out) x = fmaxf(x, 0.f);
-                        if (R) x += R[grow * ldr + gc0 + i];
+                        if (R) x = mask_res ? (R[grow * ldr + gc0 + i] > 0.f ? x : 0.f) : x + R[grow * ldr + gc0 + i];
                         C[grow * ldc + gc0 + i] = x;
                     }
                 }

@@ -72,6 +72,10 @@ struct ProfScope {
         }                                                                                          \
     } while (0)
 
+// Internal epilogue flag of the dense-layer kernels (not part of include/o4d.h): the "residual" operand R is a ReLU
+// mask -- C = R > 0 ? result : 0 -- the backward of a ReLU in front of the layer, fused into its input-gradient GEMM.
+#define O4D_MASK_RES 8
+
 #define O4D_TRY(expr)                  \
     do {                               \
         int rc__ = (expr);             \

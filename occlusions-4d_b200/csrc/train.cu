@@ -29,15 +29,6 @@ __global__ void relu_mask_kernel(const float* __restrict__ dy, const float* __re
     if (e < n) out[e] = y[e] > 0.f ? dy[e] : 0.f;
 }
 
-__global__ void mask_rows_kernel(float* __restrict__ dA, int64_t ldda, const float* __restrict__ A, int64_t lda,
-                                 int64_t rows, int k) {
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= rows * k) return;
-    const int64_t r = e / k;
-    const int c = (int)(e % k);
-    if (!(A[r * lda + c] > 0.f)) dA[r * ldda + c] = 0.f;
-}
-
 // W (n, k) ldw -> Wt (k, n) contiguous
 __global__ void transpose_kernel(const float* __restrict__ W, int64_t ldw, int n, int k, float* __restrict__ Wt) {
     __shared__ float tile[32][33];
@@ -170,8 +161,9 @@ static int colsum_splits(int64_t rows) {
 // tcgen05 weight gradient (wgrad_tc.cu)
 bool wgrad_tc_ok(int64_t rows, int64_t n, int64_t k);
 int wgrad_tc_splits(int64_t rows, int64_t n, int64_t k);
+bool wgrad_tc_aligned(const float* dY, int64_t lddy, const float* A, int64_t lda);
 int wgrad_tc_launch(const float* dY, int64_t lddy, const float* A, int64_t lda, int64_t rows, int64_t n, int64_t k,
-                    bool relu_a, int precision, float* part, int splits, cudaStream_t st);
+                    bool relu_a, int precision, float* part, float* bpart, int splits, cudaStream_t st);
 
 static int part_splits(int64_t rows, int64_t n, int64_t k) {
     int s = wgrad_splits(rows, n, k);
@@ -182,11 +174,17 @@ static int part_splits(int64_t rows, int64_t n, int64_t k) {
     return s;
 }
 
+// the tcgen05 weight gradient also produces the bias partials (one per row split)
+static int bias_splits(int64_t rows, int64_t n, int64_t k) {
+    const int c = colsum_splits(rows), p = part_splits(rows, n, k);
+    return c > p ? c : p;
+}
+
 size_t linear_bwd_ws_bytes(int64_t rows, int64_t k, int64_t n) {
     Arena a(nullptr, 0);
     a.get<float>((size_t)k * n);                                   // W^T
     a.get<float>((size_t)part_splits(rows, n, k) * n * k);         // weight-gradient partials
-    a.get<float>((size_t)colsum_splits(rows) * n);                 // bias-gradient partials
+    a.get<float>((size_t)bias_splits(rows, n, k) * n);             // bias-gradient partials
     return a.off;
 }
 
@@ -200,11 +198,12 @@ int linear_bwd_launch(const float* A, int64_t rows, int64_t k, int64_t lda, cons
     O4D_REQUIRE(!(flags & O4D_RELU_IN) || A, "linear backward: relu_in needs the forward input");
     Arena a(ws, ws_bytes);
     float* wt = a.get<float>((size_t)k * n);
-    const bool use_tc = precision != 0 && wgrad_tc_ok(rows, n, k);
+    const bool use_tc = precision != 0 && dW && wgrad_tc_ok(rows, n, k) && wgrad_tc_aligned(dY, lddy, A, lda);
     const int splits = use_tc ? wgrad_tc_splits(rows, n, k) : wgrad_splits(rows, n, k);
     float* part = a.get<float>((size_t)part_splits(rows, n, k) * n * k);
     const int csplits = colsum_splits(rows);
-    float* bpart = a.get<float>((size_t)csplits * n);
+    float* bpart = a.get<float>((size_t)bias_splits(rows, n, k) * n);
+    const bool bias_fused = use_tc && db;
     if (!a.ok || !ws) {
         set_error("linear backward: workspace too small (%zu < %zu)", ws_bytes, a.off);
         return O4D_E_WORKSPACE;
@@ -219,16 +218,16 @@ int linear_bwd_launch(const float* A, int64_t rows, int64_t k, int64_t lda, cons
         transpose_kernel<<<tg, tb, 0, st>>>(W, ldw, (int)n, (int)k, wt);
         O4D_LAUNCH_CHECK();
         // dA = dY (rows, n) . W (n, k) = dense layer with weight W^T (k, n)
-        O4D_TRY(linear_ldw_launch(dY, rows, n, lddy, wt, n, nullptr, k, nullptr, 0, dA, ldda, 0, precision, st));
-        if (flags & O4D_RELU_IN) {
-            mask_rows_kernel<<<(unsigned)cdiv(rows * k, 256), 256, 0, st>>>(dA, ldda, A, lda, rows, (int)k);
-            O4D_LAUNCH_CHECK();
-        }
+        // a ReLU in front of the layer: its backward (dA = 0 where A <= 0) rides in the GEMM epilogue as a mask operand
+        const bool mask = (flags & O4D_RELU_IN) != 0;
+        O4D_TRY(linear_ldw_launch(dY, rows, n, lddy, wt, n, nullptr, k, mask ? A : nullptr, mask ? lda : 0, dA, ldda,
+                                  mask ? O4D_MASK_RES : 0, precision, st));
     }
     if (dW) {
         ProfScope prof(PROF_LINEAR, 2.0 * (double)rows * (double)k * (double)n, st);
         if (use_tc) {
-            O4D_TRY(wgrad_tc_launch(dY, lddy, A, lda, rows, n, k, (flags & O4D_RELU_IN) != 0, precision, part, splits, st));
+            O4D_TRY(wgrad_tc_launch(dY, lddy, A, lda, rows, n, k, (flags & O4D_RELU_IN) != 0, precision, part,
+                                    bias_fused ? bpart : nullptr, splits, st));
         } else {
             int64_t rps = cdiv(cdiv(rows, splits), WG_R) * WG_R;
             dim3 grid((unsigned)cdiv(k, WG_T), (unsigned)cdiv(n, WG_T), (unsigned)splits);
@@ -241,7 +240,10 @@ int linear_bwd_launch(const float* A, int64_t rows, int64_t k, int64_t lda, cons
         reduce_partials_kernel<<<(unsigned)cdiv(n * k, 256), 256, 0, st>>>(part, splits, n * k, (int)k, dW, lddw);
         O4D_LAUNCH_CHECK();
     }
-    if (db) {
+    if (bias_fused) {
+        reduce_partials_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(bpart, splits, n, (int)n, db, n);
+        O4D_LAUNCH_CHECK();
+    } else if (db) {
         const int64_t rps = cdiv(rows, csplits);
         dim3 grid((unsigned)cdiv(n, 32), (unsigned)csplits);
         colsum_partial_kernel<<<grid, 256, 0, st>>>(dY, lddy, rows, (int)n, rps, bpart);

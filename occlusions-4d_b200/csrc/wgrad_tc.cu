@@ -1,116 +1,64 @@
 // tcgen05 weight gradient:  part[s][p][q] = sum over the rows r of split s of dY[r, p] * pre(A[r, q])
+// and (optionally, fused) the bias gradient  bpart[s][p] = sum over the same rows of dY[r, p].
 //
-// (dW = dY^T pre(A) of a dense layer Y = pre(A) W^T + b; in the reference this is the second
-// SGEMM of autograd's AddmmBackward.)  The contraction runs over ROWS, which is the slow
-// dimension of both row-major operands, so neither can be bulk-copied into a K-major UMMA
-// operand: eight producer warps read the fp32 tiles along their contiguous dimension
-// (warp-coalesced 128-byte rows), split every value into bf16 hi + lo (same bf16x3 scheme as
-// gemm_tc.cu: hi*hi + lo*hi + hi*lo in one fp32 TMEM accumulator) and store eight consecutive
-// rows of one column as one 16-byte core-matrix line -- the transpose costs nothing extra.
+// (dW = dY^T pre(A) of a dense layer Y = pre(A) W^T + b; in the reference this is the second SGEMM of autograd's
+// AddmmBackward, db the column sum next to it.)  The contraction runs over ROWS, the slow dimension of both row-major
+// operands, so the fp32 tiles cannot be bulk-copied straight into a K-major UMMA operand.  Round 1 had the converting
+// warps load them from global memory into registers: 48 loads per thread and 32-row chunk that the compiler issues in
+// dependent batches, two CTAs per SM, and ncu showed the result -- issue slots 24 % busy, long-scoreboard stalls 12.8
+// of 19 cycles per instruction, 18,000 cycles per chunk against 620 of tensor work, 40 algorithmic TFLOP/s on the
+// (240,842 x 416)^T (240,842 x 832) gradient.  This version separates the latency from the arithmetic:
 //
-//   CTA tile   : 128 (p, TMEM lanes) x BQ <= 256 (q, TMEM columns), rows walked 32 at a time
-//   warps 0-7  : producers (both operands), then the epilogue (TMEM -> fp32 partial tile)
-//   warp 8     : TMEM allocation;   warp 9 : lane 0 issues tcgen05.mma / commits
-//   grid       : (p-tiles * q-tiles, row splits); tiles of one split are adjacent in launch order
-//                so the operand rows they share are read from HBM once and hit in L2 afterwards.
-// Two CTAs per SM (2 x 96 KB smem, 2 x 256 TMEM columns).  Partials are reduced in a fixed order
-// by reduce_partials_kernel (train.cu): deterministic.
+//   warp 16 (loader)      : per 32-row chunk TWO tiled TMA loads (cp.async.bulk.tensor.2d through a tensor map per
+//                           operand: a 32 x 128 box of dY, a 32 x BQ box of A) into an fp32 staging stage; rows past the
+//                           end and columns past n / k arrive as zeros; completion by mbarrier transaction bytes; NS
+//                           (2-4) stages in flight, so ~100 KB per SM are outstanding instead of one register file's
+//                           worth.  (One cp.async.bulk per ROW was tried first: UBLKCP is a uniform-datapath instruction,
+//                           the 64 copies of a chunk issue one after the other, 4,500 cycles per chunk.)
+//   warps 0-15 (convert)  : read the staging stage along columns (conflict-free), split every value into bf16 hi + lo
+//                           (packed conversions; same bf16x3 scheme as gemm_tc.cu: hi*hi + lo*hi + hi*lo into one fp32
+//                           TMEM accumulator) and store eight consecutive ROWS of one column as one 16-byte core-matrix
+//                           line of the UMMA stage -- the transpose costs nothing extra; they also carry the running
+//                           column sums of dY for the bias gradient, and run the epilogue (TMEM -> fp32 partial tile)
+//   warp 17 (MMA)         : lane 0 issues tcgen05.mma / commits
+//   CTA tile              : 128 (p, TMEM lanes) x BQ <= 256 (q, TMEM columns); grid (p-tiles * q-tiles, row splits);
+//                           tiles of one split are adjacent in launch order, so the operand rows they share come from
+//                           HBM once and from L2 afterwards.  One CTA per SM (shared memory), at most two waves.
+// Partials are reduced in a fixed order by reduce_partials_kernel (train.cu): deterministic.
+// Requirements (wgrad_tc_ok / wgrad_tc_aligned, else the caller falls back to the fp32 kernel): 16-byte aligned operand
+// pointers, leading dimensions multiples of 4 floats (tensor-map strides), k a multiple of 4 (vector stores).
 #include "o4d_common.cuh"
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include "tc_helpers.cuh"
 
 namespace o4d {
 namespace wg {
 
-constexpr int BM = 128;
-constexpr int BK = 32;
-constexpr int STAGES = 2;
-constexpr int PROD_WARPS = 8;
-constexpr int THREADS = (PROD_WARPS + 2) * 32;
-constexpr int BQ_MAX = 256;
-constexpr int A_HALF = BM * BK * 2;                       // one bf16 image of the dY^T slab (8 KB)
-constexpr int STAGE_BYTES = 2 * A_HALF + 2 * BQ_MAX * BK * 2;   // 48 KB
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256;
+using namespace tch;
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t a, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t a) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t a, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(a), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) {
-    if (mbar_try_wait(a, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(a, parity)) {
-        if (clock64() - t0 > 4000000000LL) __trap();
-    }
-}
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
-    d |= (uint64_t)1 << 46;
-    return d;
-}
-__device__ __forceinline__ uint32_t umma_idesc(int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t mbar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-// Eight values of one operand column -> one 16-byte core-matrix line per image half.  Packed conversions
-// (tch::split_bf16x2: F2FP.BF16.F32.PACK_AB, full rate) -- the scalar F2F form ran on the quarter-rate conversion
-// pipe and made the producers, not the tensor pipe, the bound of this kernel (96 F2F per thread and 32-row chunk).
-__device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
-    tch::split_bf16x2(x[0], x[1], hi.x, lo.x);
-    tch::split_bf16x2(x[2], x[3], hi.y, lo.y);
-    tch::split_bf16x2(x[4], x[5], hi.z, lo.z);
-    tch::split_bf16x2(x[6], x[7], hi.w, lo.w);
-}
+constexpr int BK = 32;                  // rows (contraction) per chunk
+constexpr int CONV_WARPS = 16;
+constexpr int CONV_THREADS = CONV_WARPS * 32;
+constexpr int THREADS = (CONV_WARPS + 2) * 32;
+constexpr int BQ_MAX = 256;
+constexpr int NU = 2;                   // UMMA operand stages
+constexpr int NS_MAX = 4;               // fp32 staging stages
+constexpr int MAX_ITEMS = (4 * (BM + BQ_MAX) + CONV_THREADS - 1) / CONV_THREADS;   // (8-row group, column) items per thread
+constexpr int BAR_BYTES = 256;
+constexpr int SMEM_LIMIT = 227 * 1024;
+constexpr uint32_t A_HALF = BM * BK * 2;   // one bf16 image of the dY^T slab (8 KB)
 
 struct Tiling {
     int n, k;       // dW shape (p extent, q extent)
     int ptiles;     // ceil(n / 128)
     int bq, qtiles; // q tile width (multiple of 16, <= 256) and count
+    int ns;         // staging stages that fit
 };
 
-__host__ __device__ inline Tiling make_tiling(int n, int k) {
+__host__ __device__ inline int stage_bytes(int bq) { return BK * (BM + bq) * 4; }   // fp32 staging == bf16 hi + lo images
+
+inline Tiling make_tiling(int n, int k) {
     Tiling t;
     t.n = n;
     t.k = k;
@@ -120,52 +68,61 @@ __host__ __device__ inline Tiling make_tiling(int n, int k) {
     bq = (bq + 15) / 16 * 16;
     t.bq = bq;
     t.qtiles = (k + bq - 1) / bq;
+    int ns = (SMEM_LIMIT - BAR_BYTES) / stage_bytes(bq) - NU;
+    t.ns = ns > NS_MAX ? NS_MAX : ns;
     return t;
 }
 
-// One 8-row x 1-column strip of a row-major fp32 matrix -> registers (zero outside the matrix).
-template <bool RELU>
-__device__ __forceinline__ void load_strip(const float* __restrict__ X, int64_t ld, int64_t r0, int64_t r_hi, int col,
-                                           int ncols, float (&v)[8]) {
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        const int64_t r = r0 + e;
-        float x = 0.f;
-        if (col < ncols && r < r_hi) {
-            x = X[r * ld + col];
-            if (RELU) x = fmaxf(x, 0.f);
-        }
-        v[e] = x;
-    }
+// Cycle counters of one CTA (O4D_STAMPS builds only, o4d_debug_read_wgrad): which wait bounds the pipeline.
+//   [0] loader: total  [1] loader: wait for an empty staging stage   [2] converter warp 0: wait staging full
+//   [3] converter warp 0: wait UMMA stage empty  [4] converter warp 0: total loop  [5] MMA: wait UMMA stage full
+//   [6] MMA: total  [7] chunks
+__device__ long long g_dbg_wg[8];
+
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c_inner, int c_outer, uint32_t mbar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+                 "l"(tm), "r"(mbar), "r"(c_inner), "r"(c_outer)
+                 : "memory");
 }
 
 template <bool RELU>
-__global__ void __launch_bounds__(THREADS, 2)
-wgrad_tc_kernel(const float* __restrict__ dY, int64_t lddy, const float* __restrict__ A, int64_t lda, int64_t rows,
-                Tiling tl, int64_t rows_per_split, int split3, float* __restrict__ part) {
+__global__ void __launch_bounds__(THREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_a, int64_t rows, Tiling tl,
+                int64_t rows_per_split, int split3, float* __restrict__ part, float* __restrict__ bpart) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);   // full[2], empty[2], accum
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bq = tl.bq, W = BM + bq, NS = tl.ns;
+    const int sbytes = stage_bytes(bq);
+    uint8_t* ustage0 = smem + NS * sbytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (NS + NU) * sbytes);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+    const uint32_t sfull0 = smem_u32(&bars[0]), sempty0 = smem_u32(&bars[NS_MAX]);
+    const uint32_t ufull0 = smem_u32(&bars[2 * NS_MAX]), uempty0 = smem_u32(&bars[2 * NS_MAX + NU]);
+    const uint32_t accum_bar = smem_u32(&bars[2 * NS_MAX + 2 * NU]);
     const int tile = blockIdx.x;
     const int pt = tile / tl.qtiles, qt = tile % tl.qtiles;
-    const int p0 = pt * BM, q0 = qt * tl.bq;
-    const int bq = tl.bq;
+    const int p0 = pt * BM, q0 = qt * bq;
     const int64_t r_lo = (int64_t)blockIdx.y * rows_per_split;
     const int64_t r_hi = min(rows, r_lo + rows_per_split);
     const int nchunks = r_hi > r_lo ? (int)((r_hi - r_lo + BK - 1) / BK) : 0;
-    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]), accum_bar = smem_u32(&bars[2 * STAGES]);
-    const uint32_t smem_base = smem_u32(smem);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(full0 + 8 * s, PROD_WARPS);
-            mbar_init(empty0 + 8 * s, 1);
+        for (int s = 0; s < NS_MAX; ++s) {
+            mbar_init(sfull0 + 8 * s, 1);
+            mbar_init(sempty0 + 8 * s, CONV_WARPS);
+        }
+        for (int u = 0; u < NU; ++u) {
+            mbar_init(ufull0 + 8 * u, CONV_WARPS);
+            mbar_init(uempty0 + 8 * u, 1);
         }
         mbar_init(accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == PROD_WARPS) {
+    if (warp == CONV_WARPS) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -176,95 +133,154 @@ wgrad_tc_kernel(const float* __restrict__ dY, int64_t lddy, const float* __restr
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t b_half = (uint32_t)bq * BK * 2;
 
-    if (warp < PROD_WARPS) {
-        // ------------------------------------------------------------ producers
-        // thread -> column (t & 127) of each operand and the k-core pair (t >> 7): rows
-        // [16 * half, 16 * half + 16) of the 32-row chunk, i.e. kc = 2 * half, 2 * half + 1.
+    if (warp < CONV_WARPS) {
+        // ------------------------------------------------------------ converters
+        // item = (8-row group kc, column col of the staging row): eight floats down a column -> one core-matrix line
         const int t = threadIdx.x;
-        const int col = t & (BM - 1);
-        const int half = t >> 7;
+        int src[MAX_ITEMS], dst[MAX_ITEMS], pitch[MAX_ITEMS];
+        bool is_y[MAX_ITEMS];
+        float bsum[MAX_ITEMS];
+#pragma unroll
+        for (int i = 0; i < MAX_ITEMS; ++i) {
+            const int item = t + i * CONV_THREADS;
+            const int kc = item / W, col = item - kc * W;
+            const bool in = item < 4 * W;
+            const int c2 = col - BM;
+            is_y[i] = col < BM;
+            pitch[i] = is_y[i] ? BM : bq;                       // staging stage = [32][128] box of dY, then [32][bq] box of A
+            src[i] = !in ? 0 : is_y[i] ? kc * 8 * BM + col : BK * BM + kc * 8 * bq + c2;
+            dst[i] = !in ? -1
+                         : is_y[i] ? kc * (BM * 16) + (col >> 3) * 128 + (col & 7) * 16
+                                   : (int)(2 * A_HALF) + kc * (bq * 16) + (c2 >> 3) * 128 + (c2 & 7) * 16;
+            bsum[i] = 0.f;
+        }
+        const bool want_bias = bpart != nullptr && qt == 0;
+        const bool dbg = O4D_STAMPS && blockIdx.x == 0 && blockIdx.y == gridDim.y / 2 && t == 0;
+        long long t_sfull = 0, t_uempty = 0, t_start = dbg ? clock64() : 0;
         for (int c = 0; c < nchunks; ++c) {
-            const int s = c % STAGES;
-            const uint32_t ph = (uint32_t)(c / STAGES) & 1u;
-            const int64_t r0 = r_lo + (int64_t)c * BK + half * 16;
-            float ya[2][8], a0[2][8], a1[2][8];
-            const bool second = col + BM < bq;
+            const int s = c % NS, u = c % NU;
+            const uint32_t sph = (uint32_t)(c / NS) & 1u, uph = (uint32_t)(c / NU) & 1u;
+            long long tw = dbg ? clock64() : 0;
+            mbar_wait(sfull0 + 8 * s, sph);
+            if (dbg) t_sfull += clock64() - tw;
+            const float* stg = reinterpret_cast<const float*>(smem + s * sbytes);
+            float v[MAX_ITEMS][8];
 #pragma unroll
-            for (int kk = 0; kk < 2; ++kk) {
-                load_strip<false>(dY, lddy, r0 + kk * 8, r_hi, p0 + col, tl.n, ya[kk]);
-                load_strip<RELU>(A, lda, r0 + kk * 8, r_hi, (col < bq) ? q0 + col : tl.k, tl.k, a0[kk]);
-                if (second) load_strip<RELU>(A, lda, r0 + kk * 8, r_hi, q0 + col + BM, tl.k, a1[kk]);
-            }
-            mbar_wait(empty0 + 8 * s, ph ^ 1u);
-            uint8_t* a_hi = smem + s * STAGE_BYTES;
-            uint8_t* a_lo = a_hi + A_HALF;
-            uint8_t* b_hi = a_hi + 2 * A_HALF;
-            uint8_t* b_lo = b_hi + b_half;
+            for (int i = 0; i < MAX_ITEMS; ++i) {
+                if (dst[i] >= 0) {
 #pragma unroll
-            for (int kk = 0; kk < 2; ++kk) {
-                const int kc = half * 2 + kk;
-                uint4 hi, lo;
-                split8(ya[kk], hi, lo);
-                const int offa = kc * (BM * 16) + (col >> 3) * 128 + (col & 7) * 16;
-                *reinterpret_cast<uint4*>(a_hi + offa) = hi;
-                *reinterpret_cast<uint4*>(a_lo + offa) = lo;
-                if (col < bq) {
-                    split8(a0[kk], hi, lo);
-                    const int offb = kc * (bq * 16) + (col >> 3) * 128 + (col & 7) * 16;
-                    *reinterpret_cast<uint4*>(b_hi + offb) = hi;
-                    *reinterpret_cast<uint4*>(b_lo + offb) = lo;
-                }
-                if (second) {
-                    split8(a1[kk], hi, lo);
-                    const int c2 = col + BM;
-                    const int offb = kc * (bq * 16) + (c2 >> 3) * 128 + (c2 & 7) * 16;
-                    *reinterpret_cast<uint4*>(b_hi + offb) = hi;
-                    *reinterpret_cast<uint4*>(b_lo + offb) = lo;
+                    for (int e = 0; e < 8; ++e) {
+                        const float x = stg[src[i] + e * pitch[i]];       // out-of-range rows / columns were zero-filled
+                        v[i][e] = (RELU && !is_y[i]) ? fmaxf(x, 0.f) : x;
+                    }
                 }
             }
-            fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(full0 + 8 * s);
+            if (lane == 0) mbar_arrive(sempty0 + 8 * s);        // the staging values are in registers
+            if (dbg) tw = clock64();
+            mbar_wait(uempty0 + 8 * u, uph ^ 1u);
+            if (dbg) t_uempty += clock64() - tw;
+            uint8_t* ust = ustage0 + u * sbytes;
+#pragma unroll
+            for (int i = 0; i < MAX_ITEMS; ++i) {
+                if (dst[i] >= 0) {
+                    uint4 hi, lo;
+                    split_bf16x2(v[i][0], v[i][1], hi.x, lo.x);
+                    split_bf16x2(v[i][2], v[i][3], hi.y, lo.y);
+                    split_bf16x2(v[i][4], v[i][5], hi.z, lo.z);
+                    split_bf16x2(v[i][6], v[i][7], hi.w, lo.w);
+                    *reinterpret_cast<uint4*>(ust + dst[i]) = hi;
+                    if (split3) *reinterpret_cast<uint4*>(ust + dst[i] + (is_y[i] ? A_HALF : b_half)) = lo;
+                    if (want_bias && is_y[i])
+                        bsum[i] += ((v[i][0] + v[i][1]) + (v[i][2] + v[i][3])) + ((v[i][4] + v[i][5]) + (v[i][6] + v[i][7]));
+                }
+            }
+            fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ufull0 + 8 * u);
+        }
+        if (dbg) { g_dbg_wg[2] = t_sfull; g_dbg_wg[3] = t_uempty; g_dbg_wg[4] = clock64() - t_start; g_dbg_wg[7] = nchunks; }
+        // ------------------------------------------------------------ bias partial: fixed-order sum of the 4 row groups
+        if (want_bias) {
+            float* red = reinterpret_cast<float*>(smem);        // staging stage 0: every copy into it has been consumed
+            named_bar_sync(1, CONV_THREADS);
+#pragma unroll
+            for (int i = 0; i < MAX_ITEMS; ++i) {
+                const int item = t + i * CONV_THREADS;
+                if (dst[i] >= 0 && is_y[i]) red[(item / W) * BM + (item % W)] = bsum[i];
+            }
+            named_bar_sync(1, CONV_THREADS);
+            if (t < BM && p0 + t < tl.n)
+                bpart[(int64_t)blockIdx.y * tl.n + p0 + t] = (red[t] + red[BM + t]) + (red[2 * BM + t] + red[3 * BM + t]);
         }
         // ------------------------------------------------------------ epilogue
-        // warp w: TMEM lane quarter (w & 3), column half (w >> 2); one output row per thread
-        float* dst = part + (int64_t)blockIdx.y * tl.n * tl.k;
+        // warp w: TMEM lane quarter (w & 3), column quarter (w >> 2); one output row per thread
+        float* dstp = part + (int64_t)blockIdx.y * tl.n * tl.k;
         const int m = (warp & 3) * 32 + lane;
         const int gp = p0 + m;
-        const int chalf = (bq / 2 + 15) / 16 * 16;            // first half rounded to the 16-column load width
-        const int c_lo = (warp >> 2) ? chalf : 0;
-        const int c_hi = (warp >> 2) ? bq : min(chalf, bq);
+        const int cq = ((bq + 15) / 16 + 3) / 4 * 16;
+        const int c_lo = (warp >> 2) * cq;
+        const int c_hi = min(c_lo + cq, bq);
         if (nchunks > 0) {
             mbar_wait(accum_bar, 0);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
             for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
-                float v[16];
-                tmem_ld16(taddr + (uint32_t)c0, v);
+                float o[16];
+                tmem_ld16(taddr + (uint32_t)c0, o);
                 if (gp < tl.n) {
+                    float* row = dstp + (int64_t)gp * tl.k + q0 + c0;
+                    if (q0 + c0 + 16 <= tl.k) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int gq = q0 + c0 + i;
-                        if (c0 + i < bq && gq < tl.k) dst[(int64_t)gp * tl.k + gq] = v[i];
+                        for (int i = 0; i < 16; i += 4)
+                            *reinterpret_cast<float4*>(row + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (q0 + c0 + i < tl.k) row[i] = o[i];
                     }
                 }
             }
             tc_fence_before();
         } else if (gp < tl.n) {
             for (int c0 = c_lo; c0 < c_hi; ++c0)
-                if (q0 + c0 < tl.k) dst[(int64_t)gp * tl.k + q0 + c0] = 0.f;
+                if (q0 + c0 < tl.k) dstp[(int64_t)gp * tl.k + q0 + c0] = 0.f;
         }
-    } else if (warp == PROD_WARPS + 1) {
+    } else if (warp == CONV_WARPS) {
+        // ------------------------------------------------------------ loader: two tiled TMA loads per chunk
+        const bool dbg = O4D_STAMPS && blockIdx.x == 0 && blockIdx.y == gridDim.y / 2 && lane == 0;
+        long long t_wait = 0, t_start = dbg ? clock64() : 0;
+        if (lane == 0) {
+            for (int c = 0; c < nchunks; ++c) {
+                const int s = c % NS;
+                const uint32_t ph = (uint32_t)(c / NS) & 1u;
+                const long long tw = dbg ? clock64() : 0;
+                mbar_wait(sempty0 + 8 * s, ph ^ 1u);
+                if (dbg) t_wait += clock64() - tw;
+                const int r0 = (int)(r_lo + (int64_t)c * BK);
+                const uint32_t dsts = smem_u32(smem + s * sbytes);
+                mbar_arrive_expect_tx(sfull0 + 8 * s, (uint32_t)sbytes);
+                tma_load_2d(dsts, &tm_y, p0, r0, sfull0 + 8 * s);
+                tma_load_2d(dsts + BK * BM * 4, &tm_a, q0, r0, sfull0 + 8 * s);
+            }
+        }
+        if (dbg) { g_dbg_wg[0] = clock64() - t_start; g_dbg_wg[1] = t_wait; }
+    } else {
         // ------------------------------------------------------------ MMA issuer
         if (lane == 0 && nchunks > 0) {
             const uint32_t idesc = umma_idesc(bq);
             const uint32_t lbo_a = BM * 16, lbo_b = (uint32_t)bq * 16;
+            const uint32_t ubase = smem_u32(ustage0);
+            const bool dbg = O4D_STAMPS && blockIdx.x == 0 && blockIdx.y == gridDim.y / 2;
+            long long t_wait = 0, t_start = dbg ? clock64() : 0;
             for (int c = 0; c < nchunks; ++c) {
-                const int s = c % STAGES;
-                const uint32_t ph = (uint32_t)(c / STAGES) & 1u;
-                mbar_wait(full0 + 8 * s, ph);
+                const int u = c % NU;
+                const uint32_t ph = (uint32_t)(c / NU) & 1u;
+                const long long tw = dbg ? clock64() : 0;
+                mbar_wait(ufull0 + 8 * u, ph);
+                if (dbg) t_wait += clock64() - tw;
                 tc_fence_after();
-                const uint32_t a_hi = smem_base + s * STAGE_BYTES;
+                const uint32_t a_hi = ubase + u * sbytes;
                 const uint32_t a_lo = a_hi + A_HALF;
                 const uint32_t b_hi = a_hi + 2 * A_HALF;
                 const uint32_t b_lo = b_hi + b_half;
@@ -280,13 +296,14 @@ wgrad_tc_kernel(const float* __restrict__ dY, int64_t lddy, const float* __restr
                         umma_f16(tmem_base, da_hi, db_lo, idesc, 1u);
                     }
                 }
-                umma_commit(empty0 + 8 * s);
+                umma_commit(uempty0 + 8 * u);
             }
             umma_commit(accum_bar);
+            if (dbg) { g_dbg_wg[5] = t_wait; g_dbg_wg[6] = clock64() - t_start; }
         }
     }
     __syncthreads();
-    if (warp == PROD_WARPS) {
+    if (warp == CONV_WARPS) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
     }
@@ -294,12 +311,50 @@ wgrad_tc_kernel(const float* __restrict__ dY, int64_t lddy, const float* __restr
 
 }  // namespace wg
 
-bool wgrad_tc_ok(int64_t rows, int64_t n, int64_t k) { return rows >= 4096 && n >= 32 && k >= 32 && n <= 8192 && k <= 8192; }
+bool wgrad_tc_ok(int64_t rows, int64_t n, int64_t k) {
+    return rows >= 4096 && n >= 32 && k >= 32 && n <= 8192 && k <= 8192 && k % 4 == 0;
+}
+
+// Tensor maps need a 16-byte aligned base and row strides that are multiples of 16 bytes.
+bool wgrad_tc_aligned(const float* dY, int64_t lddy, const float* A, int64_t lda) {
+    return ((uintptr_t)dY % 16 == 0) && ((uintptr_t)A % 16 == 0) && lddy % 4 == 0 && lda % 4 == 0;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda).
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TensorMapEncodeFn tensor_map_encoder() {
+    static TensorMapEncodeFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (TensorMapEncodeFn)p;
+    }();
+    return fn;
+}
+
+// fp32 row-major (rows, cols) matrix with leading dimension ld; box = 32 rows x box_cols columns, zero fill outside.
+static int make_row_map(CUtensorMap* tm, const float* X, int64_t rows, int64_t cols, int64_t ld, int box_cols) {
+    TensorMapEncodeFn enc = tensor_map_encoder();
+    O4D_REQUIRE(enc != nullptr, "weight gradient: cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)wg::BK};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(X), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    O4D_REQUIRE(r == CUDA_SUCCESS, "weight gradient: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return 0;
+}
 
 int wgrad_tc_splits(int64_t rows, int64_t n, int64_t k) {
     wg::Tiling t = wg::make_tiling((int)n, (int)k);
     const int64_t tiles = (int64_t)t.ptiles * t.qtiles;
-    int64_t s = cdiv(148 * 2 * 2, tiles);            // about two waves of 2 CTAs per SM
+    int64_t s = (148 * 2) / tiles;                   // at most two full waves of one CTA per SM (no third, ragged wave)
     const int64_t max_by_rows = cdiv(rows, 1024);    // at least 32 chunks per CTA
     if (s > max_by_rows) s = max_by_rows;
     if (s > 256) s = 256;
@@ -307,21 +362,30 @@ int wgrad_tc_splits(int64_t rows, int64_t n, int64_t k) {
     return (int)s;
 }
 
-// part must hold splits * n * k floats (wgrad_tc_splits).
+// part must hold splits * n * k floats (wgrad_tc_splits); bpart (optional) splits * n floats: column sums of dY.
 int wgrad_tc_launch(const float* dY, int64_t lddy, const float* A, int64_t lda, int64_t rows, int64_t n, int64_t k,
-                    bool relu_a, int precision, float* part, int splits, cudaStream_t st) {
-    O4D_SMEM_ATTR(wg::wgrad_tc_kernel<true>, wg::SMEM_BYTES);
-    O4D_SMEM_ATTR(wg::wgrad_tc_kernel<false>, wg::SMEM_BYTES);
+                    bool relu_a, int precision, float* part, float* bpart, int splits, cudaStream_t st) {
     wg::Tiling t = wg::make_tiling((int)n, (int)k);
+    O4D_REQUIRE(t.ns >= 2, "weight gradient: tile does not fit shared memory");
+    const int smem_bytes = (t.ns + wg::NU) * wg::stage_bytes(t.bq) + wg::BAR_BYTES;
+    O4D_SMEM_ATTR(wg::wgrad_tc_kernel<true>, wg::SMEM_LIMIT);
+    O4D_SMEM_ATTR(wg::wgrad_tc_kernel<false>, wg::SMEM_LIMIT);
     const int64_t rps = cdiv(cdiv(rows, splits), wg::BK) * wg::BK;
     dim3 grid((unsigned)(t.ptiles * t.qtiles), (unsigned)splits);
     const int split3 = precision == 2 ? 0 : 1;
+    CUtensorMap tm_y, tm_a;
+    O4D_TRY(make_row_map(&tm_y, dY, rows, n, lddy, wg::BM));
+    O4D_TRY(make_row_map(&tm_a, A, rows, k, lda, t.bq));
     if (relu_a)
-        wg::wgrad_tc_kernel<true><<<grid, wg::THREADS, wg::SMEM_BYTES, st>>>(dY, lddy, A, lda, rows, t, rps, split3, part);
+        wg::wgrad_tc_kernel<true><<<grid, wg::THREADS, smem_bytes, st>>>(tm_y, tm_a, rows, t, rps, split3, part, bpart);
     else
-        wg::wgrad_tc_kernel<false><<<grid, wg::THREADS, wg::SMEM_BYTES, st>>>(dY, lddy, A, lda, rows, t, rps, split3, part);
+        wg::wgrad_tc_kernel<false><<<grid, wg::THREADS, smem_bytes, st>>>(tm_y, tm_a, rows, t, rps, split3, part, bpart);
     O4D_LAUNCH_CHECK();
     return 0;
 }
 
 }  // namespace o4d
+
+extern "C" int o4d_debug_read_wgrad(long long* out8) {
+    return (int)cudaMemcpyFromSymbol(out8, o4d::wg::g_dbg_wg, sizeof(long long) * 8);
+}

@@ -17,6 +17,7 @@
 //   and for every dense layer Y = pre(A) W^T + b:  dA = (dY W) * [A > 0 if pre = relu],
 //   dW = dY^T pre(A), db = column sums of dY.
 #include "o4d_common.cuh"
+#include <initializer_list>
 
 namespace o4d {
 
@@ -292,6 +293,23 @@ attn_u_kernel(const float* __restrict__ q, const float* __restrict__ ktab, const
     delta_vd[e] = vtab[j * d + c] + dl;
 }
 
+// the same, four channels per thread (d % 4 == 0, 16-byte aligned rows): 16-byte loads / stores
+__global__ void __launch_bounds__(256)
+attn_u_vec_kernel(const float4* __restrict__ q, const float4* __restrict__ ktab, const float4* __restrict__ vtab,
+                  const int64_t* __restrict__ nbr, int64_t n_rows, int k, int d4, float4* __restrict__ u,
+                  float4* __restrict__ delta_vd) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_rows * d4) return;
+    const int64_t row = e / d4;
+    const int c = (int)(e - row * d4);
+    const int64_t i = row / k;
+    const int64_t j = nbr[row];
+    const float4 dl = delta_vd[e];
+    const float4 qv = __ldg(q + i * d4 + c), kv = __ldg(ktab + j * d4 + c), vv = __ldg(vtab + j * d4 + c);
+    u[e] = make_float4(qv.x - kv.x + dl.x, qv.y - kv.y + dl.y, qv.z - kv.z + dl.z, qv.w - kv.w + dl.w);
+    delta_vd[e] = make_float4(vv.x + dl.x, vv.y + dl.y, vv.z + dl.z, vv.w + dl.w);
+}
+
 // per (query, channel): w = softmax_j(a * s) written over the logits; agg = sum_j w * vd
 template <int KMAX>
 __global__ void __launch_bounds__(256)
@@ -323,6 +341,46 @@ softmax_agg_train_kernel(float* __restrict__ logits_w, const float* __restrict__
             const float w = a[j] / den;
             logits_w[(i * k + j) * d + c] = w;
             num = fmaf(w, vd[(i * k + j) * d + c], num);
+        }
+    agg[e] = num;
+}
+
+// four channels per thread: the same arithmetic per channel, in the same order (bit-identical to the scalar kernel)
+template <int KMAX>
+__global__ void __launch_bounds__(128)
+softmax_agg_train_vec_kernel(float4* __restrict__ logits_w, const float4* __restrict__ vd, int64_t n, int d4, int k,
+                             float scale, float4* __restrict__ agg) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n * d4) return;
+    const int64_t i = e / d4;
+    const int c = (int)(e - i * d4);
+    float4* lw = logits_w + i * k * d4 + c;
+    const float4* vp = vd + i * k * d4 + c;
+    float4 a[KMAX];
+    float4 mx = make_float4(-3.4e38f, -3.4e38f, -3.4e38f, -3.4e38f);
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j)
+        if (j < k) {
+            const float4 x = lw[(int64_t)j * d4];
+            a[j] = make_float4(x.x * scale, x.y * scale, x.z * scale, x.w * scale);
+            mx = make_float4(fmaxf(mx.x, a[j].x), fmaxf(mx.y, a[j].y), fmaxf(mx.z, a[j].z), fmaxf(mx.w, a[j].w));
+        }
+    float4 den = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j)
+        if (j < k) {
+            a[j] = make_float4(expf(a[j].x - mx.x), expf(a[j].y - mx.y), expf(a[j].z - mx.z), expf(a[j].w - mx.w));
+            den.x += a[j].x; den.y += a[j].y; den.z += a[j].z; den.w += a[j].w;
+        }
+    float4 num = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j)
+        if (j < k) {
+            const float4 w = make_float4(a[j].x / den.x, a[j].y / den.y, a[j].z / den.z, a[j].w / den.w);
+            const float4 v = vp[(int64_t)j * d4];
+            lw[(int64_t)j * d4] = w;
+            num.x = fmaf(w.x, v.x, num.x); num.y = fmaf(w.y, v.y, num.y);
+            num.z = fmaf(w.z, v.z, num.z); num.w = fmaf(w.w, v.w, num.w);
         }
     agg[e] = num;
 }
@@ -364,6 +422,56 @@ attn_du_scatter_kernel(const float* __restrict__ du, float* __restrict__ dvd_dde
         dvd_ddelta[row * d + c] = g + gv;
     }
     dq[e] = s;
+}
+
+__global__ void __launch_bounds__(256)
+softmax_agg_bwd_vec_kernel(const float4* __restrict__ w, const float4* __restrict__ vd, const float4* __restrict__ dagg,
+                           const float4* __restrict__ agg, int64_t n_rows, int k, int d4, float scale,
+                           float4* __restrict__ da, float4* __restrict__ dvd) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_rows * d4) return;
+    const int64_t row = e / d4;
+    const int c = (int)(e - row * d4);
+    const int64_t i = row / k;
+    const float4 wv = w[e], dg = __ldg(dagg + i * d4 + c), ag = __ldg(agg + i * d4 + c), v = vd[e];
+    const float4 g = make_float4(wv.x * dg.x, wv.y * dg.y, wv.z * dg.z, wv.w * dg.w);
+    dvd[e] = g;
+    da[e] = make_float4(g.x * (v.x - ag.x) * scale, g.y * (v.y - ag.y) * scale, g.z * (v.z - ag.z) * scale,
+                        g.w * (v.w - ag.w) * scale);
+}
+
+// four channels per thread; the table gradients go out as one 16-byte vector reduction per neighbour (red.global.add.v4.f32)
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(128)
+attn_du_scatter_vec_kernel(const float4* __restrict__ du, float4* __restrict__ dvd_ddelta, const int64_t* __restrict__ nbr,
+                           int64_t n, int k, int d4, float4* __restrict__ dq, float* __restrict__ dktab,
+                           float* __restrict__ dvtab) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n * d4) return;
+    const int64_t i = e / d4;
+    const int c = (int)(e - i * d4);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < k; ++j) {
+        const int64_t row = i * k + j;
+        const int64_t jj = nbr[row];
+        const float4 g = du[row * d4 + c];
+        const float4 gv = dvd_ddelta[row * d4 + c];
+        s.x += g.x; s.y += g.y; s.z += g.z; s.w += g.w;
+        red_add_v4(dktab + (jj * d4 + c) * 4, -g.x, -g.y, -g.z, -g.w);
+        red_add_v4(dvtab + (jj * d4 + c) * 4, gv.x, gv.y, gv.z, gv.w);
+        dvd_ddelta[row * d4 + c] = make_float4(g.x + gv.x, g.y + gv.y, g.z + gv.z, g.w + gv.w);
+    }
+    dq[e] = s;
+}
+
+static inline bool vec4_ok(int d, std::initializer_list<const void*> ptrs) {
+    if (d % 4) return false;
+    for (const void* p : ptrs)
+        if ((uintptr_t)p % 16) return false;
+    return true;
 }
 
 struct AttnSaved {
@@ -435,12 +543,23 @@ int attn_train_forward(const float* const* p8, const float* q, const float* ktab
     O4D_LAUNCH_CHECK();
     // delta = Wp2 r + bp2  (into the vd buffer)
     O4D_TRY(linear_launch(s.r, rows, POS_HID_T, POS_HID_T, p8[2], p8[3], d, nullptr, 0, s.vd, d, 0, precision, st));
-    attn_u_kernel<<<(unsigned)cdiv(rows * d, 256), 256, 0, st>>>(q, ktab, vtab, nbr, rows, k, d, s.u, s.vd);
+    const bool vec = vec4_ok(d, {q, ktab, vtab, s.u, s.vd, s.w, agg});
+    if (vec)
+        attn_u_vec_kernel<<<(unsigned)cdiv(rows * (d / 4), 256), 256, 0, st>>>(
+            reinterpret_cast<const float4*>(q), reinterpret_cast<const float4*>(ktab), reinterpret_cast<const float4*>(vtab), nbr,
+            rows, k, d / 4, reinterpret_cast<float4*>(s.u), reinterpret_cast<float4*>(s.vd));
+    else
+        attn_u_kernel<<<(unsigned)cdiv(rows * d, 256), 256, 0, st>>>(q, ktab, vtab, nbr, rows, k, d, s.u, s.vd);
     O4D_LAUNCH_CHECK();
     O4D_TRY(linear_launch(s.u, rows, d, d, p8[4], p8[5], 2 * d, nullptr, 0, s.h, 2 * d, O4D_RELU_OUT, precision, st));
     O4D_TRY(linear_launch(s.h, rows, 2 * d, 2 * d, p8[6], p8[7], d, nullptr, 0, s.w, d, 0, precision, st));
-    softmax_agg_train_kernel<O4D_MAX_K><<<(unsigned)cdiv(n * d, 256), 256, 0, st>>>(
-        s.w, s.vd, n, d, k, (float)(1.0 / sqrt((double)d)), agg);
+    if (vec)
+        softmax_agg_train_vec_kernel<O4D_MAX_K><<<(unsigned)cdiv(n * (d / 4), 128), 128, 0, st>>>(
+            reinterpret_cast<float4*>(s.w), reinterpret_cast<const float4*>(s.vd), n, d / 4, k, (float)(1.0 / sqrt((double)d)),
+            reinterpret_cast<float4*>(agg));
+    else
+        softmax_agg_train_kernel<O4D_MAX_K><<<(unsigned)cdiv(n * d, 256), 256, 0, st>>>(
+            s.w, s.vd, n, d, k, (float)(1.0 / sqrt((double)d)), agg);
     O4D_LAUNCH_CHECK();
     return 0;
 }
@@ -469,8 +588,15 @@ int attn_train_backward(const float* const* p8, const float* pos, int64_t ldpos,
             if (dp8[i]) O4D_CUDA(cudaMemsetAsync(dp8[i], 0, sizes[i] * sizeof(float), st));
         return 0;
     }
-    softmax_agg_bwd_kernel<<<(unsigned)cdiv(rows * d, 256), 256, 0, st>>>(s.w, s.vd, dagg, agg, rows, k, d,
-                                                                         (float)(1.0 / sqrt((double)d)), w.da, w.dvd);
+    const bool vec = vec4_ok(d, {s.w, s.vd, dagg, agg, w.da, w.dvd, w.du, dq, dktab, dvtab});
+    if (vec)
+        softmax_agg_bwd_vec_kernel<<<(unsigned)cdiv(rows * (d / 4), 256), 256, 0, st>>>(
+            reinterpret_cast<const float4*>(s.w), reinterpret_cast<const float4*>(s.vd), reinterpret_cast<const float4*>(dagg),
+            reinterpret_cast<const float4*>(agg), rows, k, d / 4, (float)(1.0 / sqrt((double)d)),
+            reinterpret_cast<float4*>(w.da), reinterpret_cast<float4*>(w.dvd));
+    else
+        softmax_agg_bwd_kernel<<<(unsigned)cdiv(rows * d, 256), 256, 0, st>>>(s.w, s.vd, dagg, agg, rows, k, d,
+                                                                             (float)(1.0 / sqrt((double)d)), w.da, w.dvd);
     O4D_LAUNCH_CHECK();
     // a = Wa2 h + ba2   (h is post-ReLU: relu(h) = h and [h > 0] = [pre-activation > 0])
     O4D_TRY(linear_bwd_launch(s.h, rows, 2 * d, 2 * d, p8[6], 2 * d, d, w.da, d, O4D_RELU_IN, w.dh, 2 * d, dp8[6], 2 * d,
@@ -478,8 +604,13 @@ int attn_train_backward(const float* const* p8, const float* pos, int64_t ldpos,
     // h_pre = Wa1 u + ba1
     O4D_TRY(linear_bwd_launch(s.u, rows, d, d, p8[4], d, 2 * d, w.dh, 2 * d, 0, w.du, d, dp8[4], d, dp8[5], precision,
                               w.lin, w.lin_bytes, st));
-    attn_du_scatter_kernel<O4D_MAX_K><<<(unsigned)cdiv(n * d, 256), 256, 0, st>>>(w.du, w.dvd, nbr, n, k, d, dq, dktab,
-                                                                                 dvtab);
+    if (vec)
+        attn_du_scatter_vec_kernel<<<(unsigned)cdiv(n * (d / 4), 128), 128, 0, st>>>(
+            reinterpret_cast<const float4*>(w.du), reinterpret_cast<float4*>(w.dvd), nbr, n, k, d / 4,
+            reinterpret_cast<float4*>(dq), dktab, dvtab);
+    else
+        attn_du_scatter_kernel<O4D_MAX_K><<<(unsigned)cdiv(n * d, 256), 256, 0, st>>>(w.du, w.dvd, nbr, n, k, d, dq, dktab,
+                                                                                     dvtab);
     O4D_LAUNCH_CHECK();
     // delta = Wp2 r + bp2   (r post-ReLU)
     O4D_TRY(linear_bwd_launch(s.r, rows, POS_HID_T, POS_HID_T, p8[2], POS_HID_T, d, w.dvd, d, O4D_RELU_IN, w.dr,

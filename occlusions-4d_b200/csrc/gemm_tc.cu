@@ -205,8 +205,11 @@ linear_tc_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda, 
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);  // full[2], empty[2], accum
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t row0 = (int64_t)blockIdx.x * BM;
-    const int tile_n = blockIdx.y;
+    // 1-D grid, column tile fastest: the CTAs that share a 128-row slab of A are adjacent in launch order, so A comes
+    // from HBM once and from L2 for the other column tiles (with the column tile in blockIdx.y they were a whole grid
+    // row apart -- 400 MB for the attention MLP of a training frame -- and A was re-read from HBM per column tile).
+    const int64_t row0 = (int64_t)(blockIdx.x / m.ntiles) * BM;
+    const int tile_n = blockIdx.x % m.ntiles;
     const int bn = m.bn;
     const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]), accum_bar = smem_u32(&bars[2 * STAGES]);
     const uint32_t smem_base = smem_u32(smem);
@@ -274,7 +277,7 @@ linear_tc_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda, 
             }
         };
         float cur[GPW][8], nxt[GPW][8];
-        const bool dbg = O4D_STAMPS && (blockIdx.x == gridDim.x / 2) && blockIdx.y == 0 && threadIdx.x == 0;
+        const bool dbg = O4D_STAMPS && (blockIdx.x == (gridDim.x / 2 / m.ntiles) * m.ntiles) && threadIdx.x == 0;
         if (dbg) g_dbg_tc[0] = clock64();
         load_chunk(0, cur);
         for (int c = 0; c < nchunks; ++c) {
@@ -505,7 +508,7 @@ int linear_tc_packed_launch(const float* A, int64_t rows, int64_t k, int64_t lda
     // with a K-concatenated second operand the packed weight spans round32(k) + k2 columns
     const int64_t ktot = g.a2 ? cdiv(k, tc::BK) * tc::BK + g.k2 : k;
     tc::PackMeta m = tc::pack_meta((int)n, (int)ktot);
-    dim3 grid((unsigned)cdiv(rows, tc::BM), (unsigned)m.ntiles);
+    dim3 grid((unsigned)(cdiv(rows, tc::BM) * m.ntiles));
     tc::linear_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(A, rows, (int)k, lda, (const __nv_bfloat16*)packed, m, bias, R,
                                                                     ldr, C, ldc, flags, precision == 1 ? 1 : 0, g);
     O4D_LAUNCH_CHECK();

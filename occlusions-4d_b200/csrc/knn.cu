@@ -12,6 +12,7 @@
 // optionally square-rooted (sqrt is monotone but merges neighbouring values, so the
 // Euclidean ordering is evaluated on the rooted value to honour the index tie-break).
 #include "o4d_common.cuh"
+#include <stdlib.h>
 #include <math_constants.h>
 
 namespace o4d {
@@ -194,6 +195,8 @@ static int knn_dispatch_s(int S, dim3 grid_unused, const float* query, int64_t n
     switch (S) {
         O4D_KNN_CASE(1)
         O4D_KNN_CASE(4)
+        O4D_KNN_CASE(8)
+        O4D_KNN_CASE(16)
         O4D_KNN_CASE(32)
         default:
             set_error("knn: bad sub-lane count %d", S);
@@ -202,6 +205,24 @@ static int knn_dispatch_s(int S, dim3 grid_unused, const float* query, int64_t n
 #undef O4D_KNN_CASE
     O4D_LAUNCH_CHECK();
     return 0;
+}
+
+// Sub-lanes per query: enough threads to cover the machine (148 SMs x 2048 resident threads) a few times.
+// O4D_KNN_S overrides the choice (tuning: tools/time_knn.py).
+static int knn_sub_lanes(int64_t nq, int64_t m) {
+    static const int forced = [] {
+        const char* e = getenv("O4D_KNN_S");
+        const int v = e ? atoi(e) : 0;
+        return (v == 1 || v == 4 || v == 8 || v == 16 || v == 32) ? v : 0;
+    }();
+    if (forced) return forced;
+    // measured on a B200 (tools/time_knn.py, unordered points, profiles/r2_h_knn_sub_lanes.txt): a whole warp per query
+    // pays off only while the queries alone cannot fill the machine -- 14336 x 14336, K = 16: 1236 us with 32 sub-lanes,
+    // 737 us with 4; 4779 x 4779: 193 us against 248 us
+    int S = 1;
+    if (nq * 1 < 600000 && m >= 128) S = 4;
+    if (nq < 8192 && m >= 1024) S = 32;
+    return S;
 }
 
 // One scan, two neighbour lists: the k nearest by squared distance (idx32) and the k2 <= k nearest by Euclidean distance
@@ -214,9 +235,7 @@ int knn_dual_launch(const float* query, int64_t nq, int64_t ldq, const float* re
     if (nq == 0) return 0;
     O4D_REQUIRE(query && ref && idx32 && idx2 && dist2 && ldq >= 3 && ldr >= 3, "knn (two lists): bad argument");
     ProfScope prof(PROF_KNN, 8.0 * (double)nq * (double)m, st);
-    int S = 1;
-    if (nq * 1 < 600000 && m >= 128) S = 4;
-    if (nq * 4 < 600000 && m >= 1024) S = 32;
+    const int S = knn_sub_lanes(nq, m);
     KnnSecond second;
     second.k2 = k2;
     second.idx32 = idx2;
@@ -237,10 +256,7 @@ int knn_launch(const float* query, int64_t nq, int64_t ldq, const float* ref, in
     O4D_REQUIRE(idx32 || idx64 || dist, "knn: no output requested");
     O4D_REQUIRE(ldq >= 3 && ldr >= 3, "knn: leading dimensions must be >= 3");
     ProfScope prof(PROF_KNN, 8.0 * (double)nq * (double)m, st);
-    // enough threads to cover the machine (148 SMs x 2048 resident threads) a few times.
-    int S = 1;
-    if (nq * 1 < 600000 && m >= 128) S = 4;
-    if (nq * 4 < 600000 && m >= 1024) S = 32;
+    const int S = knn_sub_lanes(nq, m);
     dim3 g;
     if (k == 1) {  // nearest neighbour only (the sampler's air / solid gap filter): a single register pair
         return sqrt_dist ? knn_dispatch_s<1, true>(S, g, query, nq, ldq, ref, (int)m, ldr, k, idx32, idx64, dist, st)

@@ -270,14 +270,16 @@ class ColMeanFn(torch.autograd.Function):
 # ------------------------------------------------------------------ composed training forwards
 # (one cloud each; the nn.Modules loop over the batch exactly like their inference paths)
 
-def pt_layer_train(layer, x, pos, x2, pos2, prec=None):
-    """PointTransformerLayer.forward, point_transformer_layer.py:148-183, differentiable."""
+def pt_layer_train(layer, x, pos, x2, pos2, prec=None, nbr=None):
+    """PointTransformerLayer.forward, point_transformer_layer.py:148-183, differentiable.  `nbr`: the (n, k) neighbour
+    list of (pos, pos2) when the caller already has it (the decoder's cross-attention layers share one)."""
     if x2 is None:
         x2, pos2 = x, pos
     prec = layer.o4d_precision if prec is None else prec
     k = layer.num_neighbors
-    with torch.no_grad():
-        nbr = ops.knn(pos, pos2, k)                                            # :167
+    if nbr is None:
+        with torch.no_grad():
+            nbr = ops.knn(pos, pos2, k)                                        # :167
     q = linear(x, layer.to_q.weight, precision=prec)                          # :170
     ktab = linear(x2, layer.to_k.weight, precision=prec)                      # :171 (before the gather)
     vtab = linear(x2, layer.to_v.weight, precision=prec)                      # :172
@@ -286,11 +288,11 @@ def pt_layer_train(layer, x, pos, x2, pos2, prec=None):
     return attn_core(q, ktab, vtab, pos, pos2, nbr, k, prec, p8)               # :174-179
 
 
-def pt_block_train(block, x, pos, x2, pos2, prec=None):
+def pt_block_train(block, x, pos, x2, pos2, prec=None, nbr=None):
     """PointTransformerBlock.forward, modules.py:45-67 (x2 goes RAW into layer2 in cross mode)."""
     prec = block.o4d_precision if prec is None else prec
     y = linear(x, block.layer1.weight, block.layer1.bias, precision=prec)     # :61
-    y = pt_layer_train(block.layer2, y, pos, x2, pos2, prec)                  # :63
+    y = pt_layer_train(block.layer2, y, pos, x2, pos2, prec, nbr)             # :63
     return linear(y, block.layer3.weight, block.layer3.bias, residual=x, precision=prec)   # :64-65
 
 
@@ -359,8 +361,19 @@ def decoder_train(net, query, pcl_abstract, feat_global):
     abs_feat = pcl_abstract[:, 3:]
     query = query.detach()
     q_xyz = query[:, :3].contiguous()
+    # Every cross-attention layer searches the same (query, abstract) pair with the same K (point_transformer_layer.py:167
+    # recomputes it per layer): one scan yields that list and the local-feature list (:328), as in the inference path.
+    kc = {net.pt_blocks[i].layer2.num_neighbors for i in net.use_pt_inds.values()}
+    kc = kc.pop() if len(kc) == 1 else None
+    kl = net.num_local_features
     with torch.no_grad():
-        idx, dist = ops.knn(q_xyz, abs_xyz, net.num_local_features, sqrt_dist=True, return_dist=True)   # :328
+        nbr_c = None
+        if kc is not None and kl < kc and kc >= 9:
+            nbr_c, idx, dist = ops.knn_two_lists(q_xyz, abs_xyz, kc, kl)
+        else:
+            idx, dist = ops.knn(q_xyz, abs_xyz, kl, sqrt_dist=True, return_dist=True)                   # :328
+            if kc is not None:
+                nbr_c = ops.knn(q_xyz, abs_xyz, kc)
         pe = positional_encode(query, 0.1, net.pos_encoding_freqs) if net.pos_encoding_freqs > 0 else query
     f_loc = LocalBlendFn.apply(abs_feat, idx, dist)                            # :337-339
     x = linear(pe, net.lin_in.weight, net.lin_in.bias, precision=prec)        # :403-408
@@ -374,6 +387,6 @@ def decoder_train(net, query, pcl_abstract, feat_global):
         x = linear(h, blk.fc_1.weight, blk.fc_1.bias, residual=x, relu_in=True, precision=prec)  # :94-101
         if b in net.use_pt_inds:                                                # :421-439
             pt = net.pt_blocks[net.use_pt_inds[b]]
-            x = pt_block_train(pt, x, q_xyz, abs_feat, abs_xyz, prec)
+            x = pt_block_train(pt, x, q_xyz, abs_feat, abs_xyz, prec, nbr_c)
     out = linear(x, net.lin_out.weight, net.lin_out.bias, relu_in=True, precision=prec)          # :441-443
     return out, x

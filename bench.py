@@ -555,6 +555,62 @@ def sampler_and_loss_timing(dev):
         return {'error': '%s: %s' % (type(exc).__name__, exc)}
 
 
+def reference_train_frame(dev, cfg, abstract, glob, query, target, weights, iters=5):
+    """One decoder frame of the training step -- forward, fused loss heads, backward -- through the UNMODIFIED reference
+    module (implicit.LocalPclResnetFC.forward under torch.autograd, eager fp32 and bf16 autocast as train.py:282-296 runs
+    it) and through o4d on the same weights, inputs and loss; median of `iters` after 2 warm-ups.  The encoder is left
+    out on both sides (the reference's needs torch_cluster, absent here).  None without the reference copy."""
+    mods = reference_modules(cfg, dev)
+    if mods is None:
+        return None
+    from o4d import loss as o4d_loss
+    from tests import configs
+    loader, _, rdec = mods
+    _, odec = configs.build_modules(cfg, dev)
+    rdec.train()
+    odec.train()
+    a0, g0 = abstract.detach(), glob.detach()
+
+    def frame(dec, autocast):
+        a, g = a0.clone().requires_grad_(True), g0.clone().requires_grad_(True)
+        for p in dec.parameters():
+            p.grad = None
+        with torch.autocast('cuda', dtype=torch.bfloat16, enabled=autocast):
+            out, _ = dec(query, a, g, None)
+        heads = o4d_loss.implicit_loss_heads(out.float().reshape(query.shape[0], -1), target, 'rgb', 13, True)
+        (heads * weights).sum().backward()
+        return a.grad
+
+    def timed(dec, autocast):
+        ts = []
+        for i in range(iters + 2):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ga = frame(dec, autocast)
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= 2:
+                ts.append(e0.elapsed_time(e1))
+        return _median(ts), ga
+
+    tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with loader.quiet():
+            ref_ms, ref_ga = timed(rdec, False)
+            ref_bf16_ms, _ = timed(rdec, True)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+    o4d_ms, o4d_ga = timed(odec, False)
+    err = float((o4d_ga - ref_ga).norm() / ref_ga.norm())
+    torch.cuda.empty_cache()
+    return {'what': 'one decoder frame (%d query points, %d abstract points): forward + loss heads + backward' % (query.shape[0], a0.shape[0]),
+            'reference_eager_fp32_ms': ref_ms, 'reference_eager_bf16_autocast_ms': ref_bf16_ms, 'o4d_ms': o4d_ms,
+            'speedup_vs_reference_fp32': ref_ms / o4d_ms, 'speedup_vs_reference_bf16_autocast': ref_bf16_ms / o4d_ms,
+            'abstract_feature_gradient_rel_l2_vs_reference_autograd': err, 'kind': 'reference (oracle/_ref copy of the unmodified modules)'}
+
+
 def train_step_bench(dev, world, rank, steps):
     """BASELINE.json configs[4] per GPU: one CARLA-4D sample (14336 points), 4 frames x 17,203 query
     points (args.py:254,257 / train.py:270-274), forward + backward through the nn.Module API
@@ -611,7 +667,8 @@ def train_step_bench(dev, world, rank, steps):
             opt.step()
             return total
 
-        step()                                   # warm-up (workspaces, allocator)
+        for _ in range(3):                       # warm-up (workspaces, allocator, packed-weight cache, cold host pages)
+            step()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -633,10 +690,19 @@ def train_step_bench(dev, world, rank, steps):
 
     ms, loss = run(1)
     ms_bf16, loss_bf16 = run(2)
+    ref_frame = None
+    if rank == 0:
+        try:
+            with torch.no_grad():
+                enc0, _ = configs.build_modules(cfg, dev)
+                abstract0, glob0, _ = enc0(pcl[None], False)
+            ref_frame = reference_train_frame(dev, cfg, abstract0[0], glob0[0], queries[0], target[0], weights)
+        except Exception as exc:          # the baseline must never take the bench line down
+            ref_frame = {'error': repr(exc)[:300]}
     extras = sampler_and_loss_timing(dev) if rank == 0 else None
     flop = 3.0 * frames * per_frame * 47.9e6                      # ~3x the forward, 9.9 TFLOP per sample
     peak, _ = measured_peak()
-    return {'sampler_and_loss_heads': extras, 'ms_per_step': ms, 'samples_per_step': world, 'queries_per_sample': frames * per_frame,
+    return {'sampler_and_loss_heads': extras, 'reference_autograd_decoder_frame': ref_frame, 'ms_per_step': ms, 'samples_per_step': world, 'queries_per_sample': frames * per_frame,
             'points_per_sample': cfg['n_points'], 'query_grads_per_s': world * frames * per_frame / (ms / 1e3),
             'loss': loss, 'steps': steps, 'precision': 'bf16x3 (fp32-grade) forward and backward',
             'bf16': {'ms_per_step': ms_bf16, 'query_grads_per_s': world * frames * per_frame / (ms_bf16 / 1e3), 'loss': loss_bf16,

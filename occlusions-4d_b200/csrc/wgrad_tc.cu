@@ -24,6 +24,12 @@
 //   CTA tile              : 128 (p, TMEM lanes) x BQ <= 256 (q, TMEM columns); grid (p-tiles * q-tiles, row splits);
 //                           tiles of one split are adjacent in launch order, so the operand rows they share come from
 //                           HBM once and from L2 afterwards.  One CTA per SM (shared memory), at most two waves.
+// Measured (tools/time_wgrad.py, stamps build): 1,580 cycles per chunk, the converters busy, the loader waiting on them,
+// the MMA thread idle 46 % of the time -- 0.74 ms for the (240,842 x 416)^T (240,842 x 832) gradient (220 algorithmic
+// TFLOP/s; round 1: 4.2 ms).  Tried and rejected: staging as 32-column boxes so that every converter read is base +
+// immediate (234 instead of 293 instructions per chunk and warp) -- 11 tensor-map loads per chunk instead of 2, and one
+// thread needs ~200 cycles to issue one (2,220 cycles per chunk, loader-bound); with four loader warps 1,690 cycles,
+// still behind the two-box version.  The next lever is less conversion work per MMA (a CTA pair sharing the A tile).
 // Partials are reduced in a fixed order by reduce_partials_kernel (train.cu): deterministic.
 // Requirements (wgrad_tc_ok / wgrad_tc_aligned, else the caller falls back to the fp32 kernel): 16-byte aligned operand
 // pointers, leading dimensions multiples of 4 floats (tensor-map strides), k a multiple of 4 (vector stores).

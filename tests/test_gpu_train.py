@@ -52,6 +52,12 @@ def rel2(a, b):
     (5000, 288, 416, False, False, True, 1),
     (3000, 832, 416, False, False, False, 1),
     (2048, 32, 416, False, True, False, 1),
+    # tcgen05 weight gradient (tiled TMA loads, fused bias gradient): ragged last chunk, narrow / partial tiles, a row count
+    # that leaves the last row split short, n not a multiple of 4, four q tiles, ReLU mask folded into the dX epilogue
+    (4100, 36, 36, False, False, False, 1),
+    (4500, 100, 70, True, False, False, 1),
+    (6000, 832, 416, True, False, False, 1),
+    (9001, 416, 832, False, True, False, 1),
     (0, 16, 8, False, False, False, 0),
 ])
 def test_linear_backward_matches_autograd(rows, k, n, relu_in, relu_out, res, prec):

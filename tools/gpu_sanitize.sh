@@ -20,4 +20,10 @@ for tool in racecheck synccheck; do
       python -m pytest tests/test_gpu_kernels.py tests/test_gpu_models.py -m gpu -x -q -k "$SEL_TC" > $OUT/$tool.log 2>&1
   echo "$tool exit $?" | tee -a $OUT/$tool.log
 done
-grep -E "ERROR SUMMARY|passed|failed| exit " $OUT/*.log | tail -20
+# training path: the tcgen05 weight gradient (tensor-map loads, mbarrier rings, named barrier) and the masked dX epilogue
+for tool in memcheck synccheck; do
+  timeout 240 compute-sanitizer --tool $tool --error-exitcode 9 --print-limit 20 \
+      python -m pytest tests/test_gpu_train.py -m gpu -x -q -k "linear_backward and (4100 or 4500 or 4096)" > $OUT/${tool}_wgrad.log 2>&1
+  echo "${tool}_wgrad exit $?" | tee -a $OUT/${tool}_wgrad.log
+done
+grep -E "ERROR SUMMARY|passed|failed| exit " $OUT/*.log | tail -24

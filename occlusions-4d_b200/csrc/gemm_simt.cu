@@ -76,7 +76,7 @@ linear_simt_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda
         if (g.qa) {
             const int64_t ar = g.row_offset + gr;
             gq = g.qa + (ar / g.knbr) * n;
-            gk = g.ka + (int64_t)g.nbr[ar] * n;
+            gk = g.ka + g.neighbour(ar) * n;
         }
 #pragma unroll
         for (int j = 0; j < TN; ++j) {

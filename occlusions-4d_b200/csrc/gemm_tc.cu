@@ -339,21 +339,34 @@ linear_tc_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda, 
         constexpr int SLD = 36;                            // staging row pitch (floats): 16-byte aligned rows, conflict-free
         float* stg = reinterpret_cast<float*>(smem) + warp * (32 * SLD);
         const int rows_here = (int)min((int64_t)32, rows - warp_row0);     // may be <= 0 for a ragged last tile
-        const bool vec_ok = !g.qa && (m.n % 4 == 0) && (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) &&
+        // the row-gather term Qa[row / K] - Ka[nbr[row]] rides in the registers of the residual (never both at once here)
+        const bool gather = g.qa != nullptr;
+        const bool vec_ok = (m.n % 4 == 0) && (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) &&
                             (!R || ((ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(R) & 15) == 0))) &&
-                            (!bias || ((reinterpret_cast<uintptr_t>(bias) & 15) == 0));
+                            (!bias || ((reinterpret_cast<uintptr_t>(bias) & 15) == 0)) &&
+                            (!gather || (!R && ((reinterpret_cast<uintptr_t>(g.qa) & 15) == 0) &&
+                                         ((reinterpret_cast<uintptr_t>(g.ka) & 15) == 0)));
         if (vec_ok) {
             // write phase: lane -> (row-in-group rr, 4 columns c4): one instruction covers 4 rows x 128 B
             const int rr = lane >> 3, c4 = (lane & 7) * 4;
             float4 resn[8];
             auto load_res = [&](int c0) {
                 const int gc = col_base + c0 + c4;
-                const bool ok = R && c4 < min(32, bn - c0) && gc < m.n;
+                const bool ok = (R || gather) && c4 < min(32, bn - c0) && gc < m.n;
 #pragma unroll
                 for (int it = 0; it < 8; ++it) {
                     const int row = it * 4 + rr;
-                    resn[it] = (ok && row < rows_here) ? *reinterpret_cast<const float4*>(R + (warp_row0 + row) * ldr + gc)
-                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+                    resn[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ok && row < rows_here) {
+                        if (gather) {   // (row -> Qa / Ka rows recomputed per column block: keeping them would spill)
+                            const int64_t ar = g.row_offset + warp_row0 + row;
+                            const float4 a = __ldg(reinterpret_cast<const float4*>(g.qa + (ar / g.knbr) * m.n + gc));
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(g.ka + g.neighbour(ar) * m.n + gc));
+                            resn[it] = make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
+                        } else {
+                            resn[it] = *reinterpret_cast<const float4*>(R + (warp_row0 + row) * ldr + gc);
+                        }
+                    }
                 }
             };
             if (c_begin < c_end) load_res(c_begin);
@@ -379,8 +392,11 @@ linear_tc_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda, 
                         if (row < rows_here) {
                             float4 x = *reinterpret_cast<const float4*>(stg + row * SLD + c4);
                             x.x += bv.x; x.y += bv.y; x.z += bv.z; x.w += bv.w;
+                            if (gather) { x.x += res[it].x; x.y += res[it].y; x.z += res[it].z; x.w += res[it].w; }
                             if (relu_out) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
-                            if (mask_res) {
+                            if (gather) {
+                                // already added in front of the activation
+                            } else if (mask_res) {
                                 x.x = res[it].x > 0.f ? x.x : 0.f; x.y = res[it].y > 0.f ? x.y : 0.f;
                                 x.z = res[it].z > 0.f ? x.z : 0.f; x.w = res[it].w > 0.f ? x.w : 0.f;
                             } else {
@@ -400,7 +416,7 @@ linear_tc_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda, 
             if (g.qa && grow < rows) {
                 const int64_t ar = g.row_offset + grow;
                 gq = g.qa + (ar / g.knbr) * m.n;
-                gk = g.ka + (int64_t)g.nbr[ar] * m.n;
+                gk = g.ka + g.neighbour(ar) * m.n;
             }
             for (int c0 = c_begin; c0 < c_end; c0 += 16) {
                 float v[16];

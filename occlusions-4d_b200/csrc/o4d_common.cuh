@@ -110,9 +110,11 @@ struct Arena {
 //   C[r, c] += qa[(row_offset + r) / knbr, c] - ka[nbr[row_offset + r], c]
 // (rows are (query, neighbour) pairs; qa / ka have the layer's n columns).
 struct RowGather {
+    __host__ __device__ int64_t neighbour(int64_t r) const { return nbr ? (int64_t)nbr[r] : nbr64[r]; }
     const float* qa = nullptr;
     const float* ka = nullptr;
     const int32_t* nbr = nullptr;
+    const int64_t* nbr64 = nullptr;   // the same list as int64 (training path); exactly one of nbr / nbr64 is set
     int knbr = 1;
     int64_t row_offset = 0;
     // Optional SECOND A operand, concatenated along K behind the first one (tcgen05 path with a

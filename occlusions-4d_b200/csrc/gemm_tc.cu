@@ -297,15 +297,23 @@ linear_tc_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda, 
                 for (int i = 0; i < 4; ++i) {   // packed conversions (full rate), see tch::split_bf16x2
                     const float x0 = relu_c ? fmaxf(cur[g][2 * i], 0.f) : cur[g][2 * i];
                     const float x1 = relu_c ? fmaxf(cur[g][2 * i + 1], 0.f) : cur[g][2 * i + 1];
-                    tch::split_bf16x2(x0, x1, h[i], l[i]);
+                    if (split) {
+                        tch::split_bf16x2(x0, x1, h[i], l[i]);
+                    } else {                    // single-pass bf16 (precision 2): no low-order image at all
+                        const __nv_bfloat162 hb = __floats2bfloat162_rn(x0, x1);
+                        h[i] = *reinterpret_cast<const uint32_t*>(&hb);
+                        l[i] = 0u;
+                    }
                 }
                 // [kc][row group][row][16 B]: floats 4p..4p+3 are half (p & 1) of core-matrix line kc = p >> 1,
                 // floats 16+4p.. the same half of line kc + 2
                 const int off = (pq >> 1) * (BM * 16) + rg * 128 + rr * 16 + (pq & 1) * 8;
                 *reinterpret_cast<uint2*>(a_hi + off) = *reinterpret_cast<const uint2*>(h);
-                *reinterpret_cast<uint2*>(a_lo + off) = *reinterpret_cast<const uint2*>(l);
                 *reinterpret_cast<uint2*>(a_hi + off + 2 * (BM * 16)) = *reinterpret_cast<const uint2*>(h + 2);
-                *reinterpret_cast<uint2*>(a_lo + off + 2 * (BM * 16)) = *reinterpret_cast<const uint2*>(l + 2);
+                if (split) {
+                    *reinterpret_cast<uint2*>(a_lo + off) = *reinterpret_cast<const uint2*>(l);
+                    *reinterpret_cast<uint2*>(a_lo + off + 2 * (BM * 16)) = *reinterpret_cast<const uint2*>(l + 2);
+                }
             }
             fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
             __syncwarp();
@@ -444,8 +452,9 @@ linear_tc_kernel(const float* __restrict__ A, int64_t rows, int k, int64_t lda, 
                 const uint32_t ph = (uint32_t)(c / STAGES) & 1u;
                 mbar_wait(empty0 + 8 * s, ph ^ 1u);
                 const uint32_t dst = smem_base + s * STAGE_BYTES + 2 * A_HALF_BYTES;
-                mbar_arrive_expect_tx(full0 + 8 * s, 2 * b_half_bytes);
-                bulk_g2s(dst, wsrc + (size_t)c * 2 * b_half_bytes, 2 * b_half_bytes, full0 + 8 * s);
+                const uint32_t wbytes = split ? 2 * b_half_bytes : b_half_bytes;     // [hi][lo] per chunk: hi only at precision 2
+                mbar_arrive_expect_tx(full0 + 8 * s, wbytes);
+                bulk_g2s(dst, wsrc + (size_t)c * 2 * b_half_bytes, wbytes, full0 + 8 * s);
             }
         }
     } else {

@@ -191,12 +191,19 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant_
             for (int i = 0; i < MAX_ITEMS; ++i) {
                 if (dst[i] >= 0) {
                     uint4 hi, lo;
-                    split_bf16x2(v[i][0], v[i][1], hi.x, lo.x);
-                    split_bf16x2(v[i][2], v[i][3], hi.y, lo.y);
-                    split_bf16x2(v[i][4], v[i][5], hi.z, lo.z);
-                    split_bf16x2(v[i][6], v[i][7], hi.w, lo.w);
+                    if (split3) {
+                        split_bf16x2(v[i][0], v[i][1], hi.x, lo.x);
+                        split_bf16x2(v[i][2], v[i][3], hi.y, lo.y);
+                        split_bf16x2(v[i][4], v[i][5], hi.z, lo.z);
+                        split_bf16x2(v[i][6], v[i][7], hi.w, lo.w);
+                        *reinterpret_cast<uint4*>(ust + dst[i] + (is_y[i] ? A_HALF : b_half)) = lo;
+                    } else {                    // single-pass bf16 (precision 2): no low-order image at all
+                        const __nv_bfloat162 h0 = __floats2bfloat162_rn(v[i][0], v[i][1]), h1 = __floats2bfloat162_rn(v[i][2], v[i][3]);
+                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[i][4], v[i][5]), h3 = __floats2bfloat162_rn(v[i][6], v[i][7]);
+                        hi.x = *reinterpret_cast<const uint32_t*>(&h0); hi.y = *reinterpret_cast<const uint32_t*>(&h1);
+                        hi.z = *reinterpret_cast<const uint32_t*>(&h2); hi.w = *reinterpret_cast<const uint32_t*>(&h3);
+                    }
                     *reinterpret_cast<uint4*>(ust + dst[i]) = hi;
-                    if (split3) *reinterpret_cast<uint4*>(ust + dst[i] + (is_y[i] ? A_HALF : b_half)) = lo;
                     if (want_bias && is_y[i])
                         bsum[i] += ((v[i][0] + v[i][1]) + (v[i][2] + v[i][3])) + ((v[i][4] + v[i][5]) + (v[i][6] + v[i][7]));
                 }

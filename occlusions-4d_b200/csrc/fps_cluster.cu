@@ -11,7 +11,10 @@
 // distributed-shared-memory store each), one hardware cluster barrier (arrive.release /
 // wait.acquire) publishes them, and every thread reduces the 8 candidates itself (no second
 // block barrier).  Candidate slots are double buffered by pick parity.
-// Measured per pick at N = 14336 on a B200: single SM 1.85 us; this version 0.99 us; replacing
+// Round 2: the cluster barrier gave way to tagged candidate words that the receivers poll (0.99 -> 0.67 us per pick), then
+// the block barrier and the second-level reduce went too: every WARP publishes its candidate to all CTAs and every warp
+// reduces all of them (fps_cluster_warp_kernel, 0.57 us per pick at N = 14336, 0.47 at N = 4779; profiles/r2_h_fps_timing.txt).
+// Measured per pick at N = 14336 on a B200 in round 1: single SM 1.85 us; barrier version 0.99 us; replacing
 // the cluster barrier by remote mbarrier arrives was SLOWER (8 arrivals per CTA: 1.17 us; one per
 // warp, 128 per CTA and no block barrier: 1.36 us).  Tie rule unchanged: first (lowest-index)
 // maximum.
@@ -200,6 +203,121 @@ fps_cluster_kernel(const float* __restrict__ xyz, int n, int64_t ld, int n_out, 
     cluster_wait();
 }
 
+
+// WARP variant: no block barrier and no second-level reduce inside the pick loop.  Every warp publishes its own
+// candidate (tagged as above) to all CTAS shared memories -- lanes 0..CTAS-1 store one 8-byte word each -- and every warp
+// polls all CTAS * WARPS slots itself (lane l reads slots l, l + 32, ...), then a REDUX arg-max over the lanes gives the
+// pick.  The slot-reuse argument of POLL holds at warp granularity: a warp can write parity p of pick i + 2 only after it
+// has seen the pick-(i + 1) candidate of EVERY warp of the cluster, and a warp publishes pick i + 1 only after its own
+// last read of pick i.
+template <int CTAS, int P, int T>
+__global__ void __launch_bounds__(T, 1)
+fps_cluster_warp_kernel(const float* __restrict__ xyz, int n, int64_t ld, int n_out, int start,
+                        int32_t* __restrict__ counts, int64_t* __restrict__ order64) {
+    extern __shared__ float s_xyz[];               // sx[n], sy[n], sz[n]
+    constexpr int STRIDE = CTAS * T;
+    constexpr int NW = T / 32;                     // warps per CTA
+    constexpr int NSLOT = CTAS * NW;            // one candidate per warp of the cluster
+    constexpr int SPL = (NSLOT + 31) / 32;         // slots per lane
+    __shared__ __align__(8) uint64_t s_cand[2][NSLOT];
+    float* sx = s_xyz;
+    float* sy = s_xyz + n;
+    float* sz = s_xyz + 2 * n;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t rank = cluster_ctarank();
+
+    for (int j = tid; j < 2 * NSLOT; j += T) (&s_cand[0][0])[j] = 0ull;
+    for (int j = tid; j < n; j += T) {
+        sx[j] = xyz[(int64_t)j * ld + 0];
+        sy[j] = xyz[(int64_t)j * ld + 1];
+        sz[j] = xyz[(int64_t)j * ld + 2];
+    }
+    __syncthreads();
+    float px[P], py[P], pz[P], md[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        const int j = p * STRIDE + (int)rank * T + tid;     // ascending in p: strict '>' keeps the first maximum
+        if (j < n) {
+            px[p] = sx[j]; py[p] = sy[j]; pz[p] = sz[j];
+            md[p] = CUDART_INF_F;
+        } else {
+            px[p] = py[p] = pz[p] = 0.f;
+            md[p] = -1.f;                                          // never wins (real distances are >= 0)
+        }
+    }
+    // lane l < CTAS hands this warp's candidate to CTA l
+    uint32_t r_cand[2] = {0, 0};
+    if (lane < CTAS) {
+#pragma unroll
+        for (int b = 0; b < 2; ++b) r_cand[b] = map_remote(&s_cand[b][rank * NW + warp], (uint32_t)lane);
+    }
+    cluster_arrive();       // all CTAs are running (and have cleared their slots) before any remote access
+    cluster_wait();
+
+    int cur = start;
+    for (int it = 0; it < n_out; ++it) {
+        const float cx = sx[cur], cy = sy[cur], cz = sz[cur];
+        if (rank == 0 && tid == 0) {
+            if (order64) order64[it] = cur;
+            atomicAdd(&counts[cur], 1);
+        }
+        float bv = -1.f;
+        int bi = 0x7fffffff;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const float dd = sqdist3(px[p], py[p], pz[p], cx, cy, cz);
+            const float mm = fminf(md[p], dd);                     // padded slots keep -1
+            md[p] = mm;
+            if (mm > bv) {
+                bv = mm;
+                bi = p * STRIDE + (int)rank * T + tid;
+            }
+        }
+        {
+            const int vb = __float_as_int(bv);
+            const int vmax = __reduce_max_sync(0xffffffffu, vb);
+            bi = __reduce_min_sync(0xffffffffu, vb == vmax ? bi : 0x7fffffff);
+            bv = __int_as_float(vmax);
+        }
+        const int par = it & 1;
+        const uint32_t tag = ((uint32_t)it + 1u) & TAG_MASK;
+        if (lane < CTAS)
+            st_remote_u64_addr(r_cand[par], ((uint64_t)__float_as_uint(bv) << 32) | (tag << IDX_BITS) | ((uint32_t)bi & IDX_MASK));
+        uint64_t e[SPL];
+        long long t0 = 0;
+        for (;;) {
+            bool ok = true;
+#pragma unroll
+            for (int c = 0; c < SPL; ++c) {
+                const int slot = lane + 32 * c;
+                if (slot < NSLOT) {
+                    e[c] = ld_volatile_shared_u64(&s_cand[par][slot]);
+                    ok = ok && ((((uint32_t)e[c]) >> IDX_BITS) == tag);
+                } else {
+                    e[c] = ((uint64_t)0xBF800000u << 32) | IDX_MASK;      // value -1, sentinel index: never wins
+                }
+            }
+            if (__all_sync(0xffffffffu, ok)) break;
+            if (t0 == 0) t0 = clock64();                         // bounded: a protocol bug fails the launch instead of hanging
+            else if (clock64() - t0 > 2000000000LL) __trap();
+        }
+        float gv = -2.f;
+        int gi = 0x7fffffff;
+#pragma unroll
+        for (int c = 0; c < SPL; ++c)
+            argmax_combine(gv, gi, __uint_as_float((uint32_t)(e[c] >> 32)), (int)((uint32_t)e[c] & IDX_MASK));
+        {
+            const int vb = __float_as_int(fmaxf(gv, -1.f));      // (-2 would order above -1 as a signed integer)
+            const int vmax = __reduce_max_sync(0xffffffffu, vb);
+            gi = __reduce_min_sync(0xffffffffu, vb == vmax ? gi : 0x7fffffff);
+        }
+        cur = gi;
+    }
+    // no CTA may exit while a peer can still store into its shared memory
+    cluster_arrive();
+    cluster_wait();
+}
+
 }  // namespace fc
 
 // Returns O4D_E_UNSUPPORTED when the cloud does not fit this kernel (the caller falls back).
@@ -224,6 +342,27 @@ static int fps_cluster_launch_t(const float* xyz, int64_t n, int64_t ld, int64_t
     return 0;
 }
 
+template <int CTAS, int P, int T>
+static int fps_cluster_warp_launch_t(const float* xyz, int64_t n, int64_t ld, int64_t n_out, int64_t start, int32_t* counts,
+                                     int64_t* order64, size_t smem, cudaStream_t st) {
+    O4D_SMEM_ATTR((fc::fps_cluster_warp_kernel<CTAS, P, T>), 200 * 1024);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CTAS, 1, 1);
+    cfg.blockDim = dim3(T, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CTAS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    O4D_CUDA(cudaLaunchKernelEx(&cfg, fc::fps_cluster_warp_kernel<CTAS, P, T>, xyz, (int)n, ld, (int)n_out, (int)start, counts, order64));
+    count_launch();
+    return 0;
+}
+
 int fps_cluster_launch(const float* xyz, int64_t n, int64_t ld, int64_t n_out, int64_t start, int32_t* counts,
                        int64_t* order64, cudaStream_t st) {
     const size_t smem = (size_t)3 * n * sizeof(float);
@@ -239,14 +378,40 @@ int fps_cluster_launch(const float* xyz, int64_t n, int64_t ld, int64_t n_out, i
     const int ctas = ctas_env ? ctas_env : (n > 8192 ? 8 : 4);
     static int poll = -1;
     if (poll < 0) {
-        const char* e = getenv("O4D_FPS_SYNC");          // "barrier" = hardware cluster barrier per pick (A/B timing)
-        poll = (e && e[0] == 'b') ? 0 : 1;
+        // default: per-warp candidates, no block barrier (fps_cluster_warp_kernel).  A/B timing: "cta" = one candidate per
+        // CTA behind a block barrier, polled; "barrier" = the same with a hardware cluster barrier per pick
+        const char* e = getenv("O4D_FPS_SYNC");
+        poll = (e && e[0] == 'b') ? 0 : (e && e[0] == 'c') ? 1 : 2;
     }
     if (n > (int64_t)fc::IDX_MASK) poll = 0;             // the tagged candidate word holds 18 index bits
+    static int threads_env = -1;
+    if (threads_env < 0) {
+        const char* e = getenv("O4D_FPS_THREADS");       // 256: half the warps per CTA (per-warp exchange only; A/B timing)
+        threads_env = e ? atoi(e) : 0;
+    }
+    if (poll == 2 && threads_env == 256) {
+        const int ppt2 = (int)cdiv(n, (int64_t)ctas * 256);
+#define O4D_FW(C, PV) return fps_cluster_warp_launch_t<C, PV, 256>(xyz, n, ld, n_out, start, counts, order64, smem, st)
+        if (ctas == 8) {
+            if (ppt2 <= 2) O4D_FW(8, 2);
+            if (ppt2 <= 4) O4D_FW(8, 4);
+            if (ppt2 <= 8) O4D_FW(8, 8);
+            if (ppt2 <= 10) O4D_FW(8, 10);
+        } else if (ctas == 4) {
+            if (ppt2 <= 4) O4D_FW(4, 4);
+            if (ppt2 <= 8) O4D_FW(4, 8);
+            if (ppt2 <= 16) O4D_FW(4, 16);
+            if (ppt2 <= 18) O4D_FW(4, 18);
+        }
+#undef O4D_FW
+    }
     const int ppt = (int)cdiv(n, (int64_t)ctas * fc::THREADS);
-#define O4D_FC(C, PV)                                                                                            \
-    return poll ? fps_cluster_launch_t<C, PV, true>(xyz, n, ld, n_out, start, counts, order64, smem, st)        \
-                : fps_cluster_launch_t<C, PV, false>(xyz, n, ld, n_out, start, counts, order64, smem, st)
+#define O4D_FC(C, PV)                                                                                                \
+    {                                                                                                                \
+        if (poll == 2) return fps_cluster_warp_launch_t<C, PV, fc::THREADS>(xyz, n, ld, n_out, start, counts, order64, smem, st); \
+        return poll ? fps_cluster_launch_t<C, PV, true>(xyz, n, ld, n_out, start, counts, order64, smem, st)        \
+                    : fps_cluster_launch_t<C, PV, false>(xyz, n, ld, n_out, start, counts, order64, smem, st);      \
+    }
     if (ctas == 8) {
         if (ppt <= 1) O4D_FC(8, 1);
         if (ppt <= 2) O4D_FC(8, 2);

@@ -366,7 +366,8 @@ static int fps_cluster_warp_launch_t(const float* xyz, int64_t n, int64_t ld, in
 int fps_cluster_launch(const float* xyz, int64_t n, int64_t ld, int64_t n_out, int64_t start, int32_t* counts,
                        int64_t* order64, cudaStream_t st) {
     const size_t smem = (size_t)3 * n * sizeof(float);
-    if (n <= 2048 || smem > 200 * 1024) return O4D_E_UNSUPPORTED;
+    static const int64_t min_n = getenv("O4D_FPS_CLUSTER_MIN") ? atoll(getenv("O4D_FPS_CLUSTER_MIN")) : 1024;   // below: the single-SM kernel
+    if (n <= min_n || smem > 200 * 1024) return O4D_E_UNSUPPORTED;
     static int ctas_env = -1;
     if (ctas_env < 0) {
         const char* e = getenv("O4D_FPS_CTAS");          // force a cluster size: 2, 4 or 8
@@ -386,8 +387,11 @@ int fps_cluster_launch(const float* xyz, int64_t n, int64_t ld, int64_t n_out, i
     if (n > (int64_t)fc::IDX_MASK) poll = 0;             // the tagged candidate word holds 18 index bits
     static int threads_env = -1;
     if (threads_env < 0) {
-        const char* e = getenv("O4D_FPS_THREADS");       // 256: half the warps per CTA (per-warp exchange only; A/B timing)
-        threads_env = e ? atoi(e) : 0;
+        // threads per CTA of the per-warp exchange: every pick waits for the slowest warp of the cluster, so FEWER warps
+        // are faster until the distance update of P points per thread takes over (profiles/r2_h_fps_timing.txt:
+        // 512 threads 0.57 us per pick at N = 14336, 256: 0.44, 128: 0.39, 64: 0.50).  A/B timing: 256, 512
+        const char* e = getenv("O4D_FPS_THREADS");
+        threads_env = e ? atoi(e) : 128;
     }
     if (poll == 2 && threads_env == 256) {
         const int ppt2 = (int)cdiv(n, (int64_t)ctas * 256);
@@ -402,6 +406,22 @@ int fps_cluster_launch(const float* xyz, int64_t n, int64_t ld, int64_t n_out, i
             if (ppt2 <= 8) O4D_FW(4, 8);
             if (ppt2 <= 16) O4D_FW(4, 16);
             if (ppt2 <= 18) O4D_FW(4, 18);
+        }
+#undef O4D_FW
+    }
+    if (poll == 2 && threads_env == 128) {
+        const int ppt2 = (int)cdiv(n, (int64_t)ctas * 128);
+#define O4D_FW(C, PV) return fps_cluster_warp_launch_t<C, PV, 128>(xyz, n, ld, n_out, start, counts, order64, smem, st)
+        if (ctas == 8) {
+            if (ppt2 <= 5) O4D_FW(8, 5);
+            if (ppt2 <= 10) O4D_FW(8, 10);
+            if (ppt2 <= 14) O4D_FW(8, 14);
+            if (ppt2 <= 20) O4D_FW(8, 20);
+        } else if (ctas == 4) {
+            if (ppt2 <= 10) O4D_FW(4, 10);
+            if (ppt2 <= 16) O4D_FW(4, 16);
+            if (ppt2 <= 28) O4D_FW(4, 28);
+            if (ppt2 <= 36) O4D_FW(4, 36);
         }
 #undef O4D_FW
     }

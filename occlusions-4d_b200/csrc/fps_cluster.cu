@@ -389,7 +389,8 @@ int fps_cluster_launch(const float* xyz, int64_t n, int64_t ld, int64_t n_out, i
     if (threads_env < 0) {
         // threads per CTA of the per-warp exchange: every pick waits for the slowest warp of the cluster, so FEWER warps
         // are faster until the distance update of P points per thread takes over (profiles/r2_h_fps_timing.txt:
-        // 512 threads 0.57 us per pick at N = 14336, 256: 0.44, 128: 0.39, 64: 0.50).  A/B timing: 256, 512
+        // 512 threads 0.57 us per pick at N = 14336, 256: 0.44, 128: 0.39, 64: 0.50; a 16-CTA (non-portable) cluster of
+        // 128 threads: 0.42 -- more candidate words to wait for than distance work saved).  A/B timing: 256, 512
         const char* e = getenv("O4D_FPS_THREADS");
         threads_env = e ? atoi(e) : 128;
     }

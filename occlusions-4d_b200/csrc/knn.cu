@@ -97,12 +97,34 @@ knn_kernel(const float* __restrict__ query, int64_t nq, int64_t ldq,
             sz[t] = r[2];
         }
         __syncthreads();
-        if (live) {
-            for (int t = sub; t < cnt; t += S) {
-                float dx = qx - sx[t], dy = qy - sy[t], dz = qz - sz[t];
-                float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-                if (SQRT) d2 = __fsqrt_rn(d2);
-                top.push(d2, base + t);
+        // Two phases per block of 32 candidates of a thread (warp-uniform trip counts).  Phase 1 only FILTERS against the
+        // thread's current K-th best (a bit per candidate, no divergence); phase 2 inserts the survivors, lowest index
+        // first, recomputing their distance.  With unordered queries nearly every candidate used to send the whole warp
+        // down the ~60-instruction sorted insertion (some lane inserts); now the warp runs it max-over-lanes(survivors)
+        // times per block.  Results are unchanged: the filter bound is never tighter than the one push() applies, and the
+        // insertion order within a thread is still ascending.
+        auto dist = [&](int t) {
+            const float dx = qx - sx[t], dy = qy - sy[t], dz = qz - sz[t];
+            float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            if (SQRT) d2 = __fsqrt_rn(d2);
+            return d2;
+        };
+        for (int blk = 0; blk * (S * 32) < cnt; ++blk) {
+            const int t0 = blk * (S * 32) + sub;
+            const float tau = top.d[KMAX - 1];
+            unsigned pend = 0;
+#pragma unroll
+            for (int b = 0; b < 32; ++b) {
+                const int t = t0 + S * b;
+                if (live && t < cnt && dist(t) < tau) pend |= 1u << b;
+            }
+            while (__any_sync(0xffffffffu, pend != 0)) {
+                if (pend) {
+                    const int b = __ffs(pend) - 1;
+                    pend &= pend - 1;
+                    const int t = t0 + S * b;
+                    top.push(dist(t), base + t);
+                }
             }
         }
     }
@@ -216,12 +238,16 @@ static int knn_sub_lanes(int64_t nq, int64_t m) {
         return (v == 1 || v == 4 || v == 8 || v == 16 || v == 32) ? v : 0;
     }();
     if (forced) return forced;
-    // measured on a B200 (tools/time_knn.py, unordered points, profiles/r2_h_knn_sub_lanes.txt): a whole warp per query
-    // pays off only while the queries alone cannot fill the machine -- 14336 x 14336, K = 16: 1236 us with 32 sub-lanes,
-    // 737 us with 4; 4779 x 4779: 193 us against 248 us
+    // measured on a B200 (tools/time_knn.py, unordered points, profiles/r2_h_knn_sub_lanes.txt): more sub-lanes pay off
+    // only while the queries alone cannot fill the machine -- 14336 x 14336, K = 16: 361 us with 4 sub-lanes, 673 us with
+    // 32; 4779 x 14336: 228 us with 8 (4: 307, 32: 277); 1593 x 4779: 68 us with 16; 531 x 531: 22 us with 32
     int S = 1;
-    if (nq * 1 < 600000 && m >= 128) S = 4;
-    if (nq < 8192 && m >= 1024) S = 32;
+    if (nq < 600000 && m >= 128) S = 4;
+    if (m >= 1024) {
+        if (nq < 8192) S = 8;
+        if (nq < 3000) S = 16;
+        if (nq < 1024) S = 32;
+    }
     return S;
 }
 

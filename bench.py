@@ -644,6 +644,8 @@ def train_step_bench(dev, world, rank, steps):
     target = target.to(dev)
     weights = torch.tensor([1.0, 1.0, 0.6, 1.0], device=dev)        # color, density, segmentation, tracking
 
+    each = []
+
     def run(precision):
         # the inference legs before this one leave the caching allocator full of differently sized blocks; without this
         # the first precision timed pays cudaMalloc / cudaFree churn inside its steps (seen as 110-200 ms instead of 84)
@@ -677,13 +679,14 @@ def train_step_bench(dev, world, rank, steps):
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        evs[0].record()
+        for i in range(steps):
             total = step()
-        e1.record()
+            evs[i + 1].record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / steps
+        ms = evs[0].elapsed_time(evs[steps]) / steps
+        each.append([round(evs[i].elapsed_time(evs[i + 1]), 2) for i in range(steps)])
         if world > 1:
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -709,8 +712,8 @@ def train_step_bench(dev, world, rank, steps):
     peak, _ = measured_peak()
     return {'sampler_and_loss_heads': extras, 'reference_autograd_decoder_frame': ref_frame, 'ms_per_step': ms, 'samples_per_step': world, 'queries_per_sample': frames * per_frame,
             'points_per_sample': cfg['n_points'], 'query_grads_per_s': world * frames * per_frame / (ms / 1e3),
-            'loss': loss, 'steps': steps, 'precision': 'bf16x3 (fp32-grade) forward and backward',
-            'bf16': {'ms_per_step': ms_bf16, 'query_grads_per_s': world * frames * per_frame / (ms_bf16 / 1e3), 'loss': loss_bf16,
+            'loss': loss, 'steps': steps, 'ms_each_step': each[0], 'precision': 'bf16x3 (fp32-grade) forward and backward',
+            'bf16': {'ms_per_step': ms_bf16, 'ms_each_step': each[1], 'query_grads_per_s': world * frames * per_frame / (ms_bf16 / 1e3), 'loss': loss_bf16,
                      'precision': 'single-pass bf16 operands, fp32 accumulation, fp32 master weights (BASELINE config 5 "bf16")',
                      'roofline': {'bound': 'tensor', 'achieved': flop / (ms_bf16 / 1e3) / 1e12, 'peak': peak, 'unit': 'TFLOP/s',
                                   'frac': flop / (ms_bf16 / 1e3) / 1e12 / peak}},

@@ -521,7 +521,7 @@ int tc_pack_pair_launch(const float* W, int64_t n, int64_t k, int64_t ldw, void*
 
 // n >= 8: narrow outputs (lin_out, 9 .. 33 columns) run as one 16/32/48-column UMMA tile; the CUDA-core kernel
 // took as long for 416 -> 9 as the tensor-core kernel for 416 -> 416 (69 us per 32768 rows).
-bool tc_shape_ok(int64_t rows, int64_t k, int64_t n) { return rows >= 1024 && k >= 32 && n >= 4 && k <= 65536 && n <= 65536; }
+bool tc_shape_ok(int64_t rows, int64_t k, int64_t n) { return rows >= 512 && k >= 32 && n >= 4 && k <= 65536 && n <= 65536; }
 
 int linear_tc_packed_launch(const float* A, int64_t rows, int64_t k, int64_t lda, const void* packed, int64_t n,
                             const float* bias, const float* R, int64_t ldr, float* C, int64_t ldc, int flags,

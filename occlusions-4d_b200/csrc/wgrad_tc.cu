@@ -325,7 +325,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant_
 }  // namespace wg
 
 bool wgrad_tc_ok(int64_t rows, int64_t n, int64_t k) {
-    return rows >= 4096 && n >= 32 && k >= 32 && n <= 8192 && k <= 8192 && k % 4 == 0;
+    return rows >= 1024 && n >= 32 && k >= 32 && n <= 8192 && k <= 8192 && k % 4 == 0;
 }
 
 // Tensor maps need a 16-byte aligned base and row strides that are multiples of 16 bytes.

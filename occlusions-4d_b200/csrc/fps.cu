@@ -111,6 +111,7 @@ fps_kernel(const float* __restrict__ xyz, int n, int64_t ld, int n_out, int star
                 v = __int_as_float(vmax);
             }
             if (lane == 0) {
+                if (i >= n) i = 0;              // all-NaN cloud: the sentinel index must not reach the loads below
                 s_cur = i;
                 s_c[0] = xyz[(int64_t)i * ld + 0];
                 s_c[1] = xyz[(int64_t)i * ld + 1];
@@ -202,7 +203,7 @@ fps_big_kernel(const float* __restrict__ xyz, int n, int64_t ld, int n_out, int 
                 i = __reduce_min_sync(0xffffffffu, vb == vmax ? i : 0x7fffffff);
                 v = __int_as_float(vmax);
             }
-            if (lane == 0) s_cur = i;
+            if (lane == 0) s_cur = i < n ? i : 0;      // (all-NaN cloud: stay inside the arrays)
         }
         __syncthreads();
     }

@@ -194,7 +194,7 @@ fps_cluster_kernel(const float* __restrict__ xyz, int n, int64_t ld, int n_out, 
                 argmax_combine(gv, gi, __uint_as_float((uint32_t)(e >> 32)), (int)(uint32_t)(e & 0xffffffffu));
             }
         }
-        cur = gi;
+        cur = gi < n ? gi : 0;      // all-NaN clouds keep the sentinel: stay inside the coordinate arrays
         // s_val / s_idx are rewritten only after the next distance update and s_cand[parity] only two
         // picks later (see POLL above / separated from these reads by a cluster barrier).
     }
@@ -311,7 +311,7 @@ fps_cluster_warp_kernel(const float* __restrict__ xyz, int n, int64_t ld, int n_
             const int vmax = __reduce_max_sync(0xffffffffu, vb);
             gi = __reduce_min_sync(0xffffffffu, vb == vmax ? gi : 0x7fffffff);
         }
-        cur = gi;
+        cur = gi < n ? gi : 0;      // all-NaN clouds keep the sentinel: stay inside the coordinate arrays
     }
     // no CTA may exit while a peer can still store into its shared memory
     cluster_arrive();

@@ -154,6 +154,9 @@ knn_kernel(const float* __restrict__ query, int64_t nq, int64_t ldq,
         } else {
             top.pop_front();
         }
+        // fewer than k finite distances (NaN / Inf coordinates): the slot keeps the sentinel -- emit a valid row index (0)
+        // so that the gathers downstream stay inside their tables; the distance stays +Inf
+        if (bi >= m) bi = 0;
         md[r] = bd;
         mi[r] = bi;
         if (live && sub == 0) {
@@ -196,7 +199,7 @@ knn_kernel(const float* __restrict__ query, int64_t nq, int64_t ldq,
 #pragma unroll
         for (int t = 0; t < KMAX; ++t)
             if (t < k2) {
-                if (second.idx32) second.idx32[qi * k2 + t] = mi[t];
+                if (second.idx32) second.idx32[qi * k2 + t] = mi[t] < m ? mi[t] : 0;      // (sentinel: see above)
                 if (second.dist) second.dist[qi * k2 + t] = sr[t];
             }
     }

@@ -117,7 +117,8 @@ O4D_HD RowInfo classify(const Head& hd, const float* t) {
     ri.color = solid && (t[1] >= 0.f);
     ri.track = hd.track_idx >= 0 && solid && (t[4] >= 0.f);
     ri.tag = (int)t[5];                          // .type(torch.int64) truncates
-    ri.segm = hd.semantic_classes > 0 && ri.tag >= 0;
+    // (a tag >= semantic_classes makes torch's cross_entropy raise; here the point is left out instead of read past z)
+    ri.segm = hd.semantic_classes > 0 && ri.tag >= 0 && ri.tag < hd.semantic_classes;
     ri.vivid = false;
     ri.cls = 0;
     ri.sat = ri.val = 0.f;

@@ -67,6 +67,26 @@ def test_knn_matches_oracle(nq, m, k, sqrt):
     assert torch.equal(dist.cpu(), od)
 
 
+def test_non_finite_coordinates_stay_inside_the_tables():
+    """NaN / Inf coordinates never pass a distance comparison: the emitted neighbour indices and FPS picks must still be
+    valid row numbers (the gathers downstream index tables with them), and finite rows keep their exact result."""
+    g = torch.Generator().manual_seed(3)
+    q = torch.rand(500, 3, generator=g)
+    ref = torch.rand(40, 3, generator=g)
+    ref[5:] = float('nan')                                   # only 5 finite reference points, k = 14
+    idx, dist = ops.knn(q.to(DEV), ref.to(DEV), 14, sqrt_dist=True, return_dist=True)
+    assert int(idx.min()) >= 0 and int(idx.max()) < 40
+    want = torch.cdist(q.double(), ref[:5].double()).sort(dim=1)
+    assert torch.equal(idx[:, :5].cpu(), want.indices)
+    assert bool(torch.isinf(dist[:, 5:]).all())
+    i1, i2, _ = ops.knn_two_lists(q.to(DEV), ref.to(DEV), 14, 8)
+    assert int(i1.min()) >= 0 and int(i1.max()) < 40 and int(i2.min()) >= 0 and int(i2.max()) < 40
+    for n in (700, 3000):                                    # single-SM kernel and the cluster kernel
+        cloud = torch.full((n, 3), float('nan'))
+        picks = ops.fps(cloud.to(DEV), n // 3, 0)
+        assert int(picks.min()) >= 0 and int(picks.max()) < n
+
+
 def test_knn_encoder_self_shape_bit_exact():
     g = torch.Generator().manual_seed(14336)
     p = torch.rand(14336, 3, generator=g) * 10 - 5

@@ -614,6 +614,28 @@ def reference_train_frame(dev, cfg, abstract, glob, query, target, weights, iter
             'abstract_feature_and_global_gradient_rel_l2_vs_reference_autograd': err, 'kind': 'reference (oracle/_ref copy of the unmodified modules)'}
 
 
+def warm_up_until_quiet(step, alloc_count, world, dev, min_steps=3, max_steps=12):
+    """Runs step() until one step makes at most one device allocation (alloc_count() = running number of cudaMalloc
+    calls of this rank), at least min_steps and at most max_steps times; returns the number of steps run.  Every step
+    contains a collective when world > 1 (the gradient all-reduce), so the decision to go on is itself agreed across
+    the ranks (MAX): all ranks run the SAME number of steps -- ranks leaving the loop at different times deadlock
+    the next collective (seen once on 2 GPUs: an all-reduce of the gradients against the barrier of the faster rank)."""
+    import torch.distributed as dist
+    n = 0
+    while n < max_steps:
+        before = alloc_count()
+        step()
+        n += 1
+        more = 1 if (n < min_steps or alloc_count() - before > 1) else 0
+        if world > 1:
+            flag = torch.tensor([more], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+            more = int(flag.item())
+        if not more:
+            break
+    return n
+
+
 def train_step_bench(dev, world, rank, steps):
     """BASELINE.json configs[4] per GPU: one CARLA-4D sample (14336 points), 4 frames x 17,203 query
     points (args.py:254,257 / train.py:270-274), forward + backward through the nn.Module API
@@ -678,13 +700,7 @@ def train_step_bench(dev, world, rank, steps):
         # warm-up (workspaces, packed-weight cache, cold host pages) until the caching allocator has stopped growing:
         # after the inference legs it needs ~7 steps of ~20 cudaMalloc calls each to settle on this step's block sizes,
         # and a cudaMalloc of a multi-GB segment blocks the host for 100-300 ms (seen as single 150-420 ms steps)
-        warm_steps = 0
-        while warm_steps < 12:
-            n_a = torch.cuda.memory_stats(dev).get('num_device_alloc', 0)
-            step()
-            warm_steps += 1
-            if warm_steps >= 3 and torch.cuda.memory_stats(dev).get('num_device_alloc', 0) - n_a <= 1:
-                break
+        warm_steps = warm_up_until_quiet(step, lambda: torch.cuda.memory_stats(dev).get('num_device_alloc', 0), world, dev)
         gc.collect()                             # ... and no cycle-collector pass inside the timed steps either
         gc.disable()
         torch.cuda.synchronize()

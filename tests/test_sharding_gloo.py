@@ -5,6 +5,7 @@ plumbing runs with the CUDA decoder and NCCL (tests/test_gpu_models.py, bench.py
 import os
 import sys
 
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -62,3 +63,47 @@ def test_sharded_decode_equals_single_rank_gloo():
         ret = mgr.dict()
         mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
         assert dict(ret) == {0: True, 1: True}
+
+
+def _warmup_worker(rank, world, port, ret):
+    if REPO not in sys.path:
+        sys.path.insert(0, REPO)
+    import bench
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    # every step holds a collective (the gradient all-reduce of the training step); the two ranks' allocators settle at
+    # different steps: rank 0 after 3, rank 1 after 6
+    quiet_after = 3 if rank == 0 else 6
+    state = {'steps': 0, 'allocs': 0}
+
+    def step():
+        state['steps'] += 1
+        state['allocs'] += 20 if state['steps'] <= quiet_after else 0
+        t = torch.ones(4)
+        dist.all_reduce(t)                       # mismatched step counts would pair this with the barrier below
+
+    n = bench.warm_up_until_quiet(step, lambda: state['allocs'], world, 'cpu')
+    dist.barrier()
+    ret[rank] = (n, state['steps'])
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_adaptive_warm_up_runs_the_same_number_of_steps_on_every_rank_gloo():
+    """bench.train_step_bench warms up until the caching allocator is quiet; the step count must be agreed across
+    ranks, or the ranks' collectives pair up wrongly and hang (it did, once, on 2 GPUs)."""
+    world = 2
+    port = 31500 + (os.getpid() % 2000)
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_warmup_worker, args=(world, port, ret), nprocs=world, join=True)
+        assert dict(ret) == {0: (7, 7), 1: (7, 7)}      # rank 1 needs 6 noisy steps + 1 quiet one; rank 0 follows
+    # single process: stops on its own count, bounded by max_steps
+    import bench
+    calls = {'n': 0, 'a': 0}
+
+    def step():
+        calls['n'] += 1
+        calls['a'] += 5
+    assert bench.warm_up_until_quiet(step, lambda: calls['a'], 1, 'cpu') == 12

@@ -248,9 +248,8 @@ class LocalPclResnetFC(ResnetFC):
             assert points_query.shape[0] == pcl_abstract.shape[0]
             assert points_query.shape[0] == features_global.shape[0]
             B = points_query.shape[0]
-            if B != 1:
-                print(points_query.shape, pcl_abstract.shape, features_global.shape)
-            assert B == 1
+            assert B == 1, 'local attention mode takes one scene at a time (implicit.py:317), got shapes %s %s %s' % (
+                tuple(points_query.shape), tuple(pcl_abstract.shape), tuple(features_global.shape))
             if self.local_mode == 'attention':
                 assert points_query.shape[-1] == self.d_in
                 assert features_global.shape[-1] + self.d_latent_local == self.d_latent

@@ -39,6 +39,44 @@ def test_committed_bench_line_follows_the_contract(name):
         assert t['tf32'] is False and t['o4d_over_torch_eager'] > 10.0 and t['max_rel_err_vs_torch_eager'] < 1e-3
 
 
+@pytest.mark.parametrize('name', ['r2_j_bench.json', 'r2_k_bench_final.json'])
+def test_round2_bench_lines_carry_the_round2_keys(name):
+    """The full-round lines of round 2: the contract keys plus the real-reference baselines, config-3 / config-4 /
+    config-5 keys and their internal consistency."""
+    line = json.loads(open(os.path.join(REPO, 'profiles', name)).read().strip().splitlines()[-1])
+    for key in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
+                'vs_baseline', 'dtype', 'data', 'config', 'e2e', 'gpu_launches', 'clocks', 'roofline', 'cpu_baseline',
+                'torch_gpu_baseline', 'encoder', 'carla_config3', 'strong_scaling', 'train_step', 'kernel_families'):
+        assert key in line, key
+    assert line['dtype'] == 'bf16x3' and line['vs_baseline'] is None and line['warmup'] >= 3
+    q = line['queries_per_step_per_gpu'] * line['n_gpus']
+    assert abs(line['value'] - q / (line['ms_per_step'] / 1e3)) / line['value'] < 1e-6
+    roof = line['roofline']
+    assert roof['bound'] == 'tensor' and abs(roof['frac'] - roof['achieved'] / roof['peak']) < 1e-9
+    fam = line['kernel_families']
+    assert roof['kernel'] in fam and sum(f['ms'] for f in fam.values()) < line['ms_per_step']
+    assert abs(roof['share_of_step'] - fam[roof['kernel']]['ms'] / sum(f['ms'] for f in fam.values())) < 1e-6
+    assert line['cpu_baseline']['kind'] == 'reference' and line['cpu_baseline']['cores'] >= 1
+    t = line['torch_gpu_baseline']
+    assert t['kind'] == 'reference' and t['tf32'] is False and t['warmup_passes'] == 10 and t['timed_passes'] == 20
+    assert t['o4d_over_torch_eager'] > 10.0                                   # the north star's own target
+    err = t['rel_err_o4d_vs_reference_all_queries']
+    assert err['rows'] == 534528 and err['p9999'] < 1e-4 and err['rows_above_1e-3'] <= 4   # near-tie neighbour flips only
+    assert line['e2e']['bit_identical_to_device_path'] is True
+    enc = line['encoder']
+    assert enc['ms'] < 8.0 and enc['critical_path']['ms'] < enc['ms'] and enc['reference']['gpu_eager']['kind'] == 'reference'
+    c3 = line['carla_config3']
+    assert c3['m_abstract'] == 2124 and c3['d_out'] == 18 and c3['max_rel_err_vs_reference_golden'] < 1e-3
+    ss = line['strong_scaling']
+    assert ss['queries'] == 2097152 and set(ss['by_batch']) == {'8192', '32768', '131072'}
+    assert ss['sharded_equals_single_rank_bitwise'] is True and ss['max_abs_diff_sharded_vs_single'] == 0.0
+    tr = line['train_step']
+    assert tr['queries_per_sample'] == 4 * 17203 and tr['ms_per_step'] < 166.0 and 'bf16' in tr and 'roofline' in tr
+    ref = tr['reference_autograd_decoder_frame']
+    assert ref['kind'].startswith('reference') and ref['speedup_vs_reference_fp32'] > 3.0
+    assert ref['abstract_feature_and_global_gradient_rel_l2_vs_reference_autograd'] < 1e-3
+
+
 def test_reference_arm_line_follows_the_contract():
     line = json.loads(open(os.path.join(REPO, 'profiles', 'r1_j_bench_reference_cpu.json')).read().strip().splitlines()[-1])
     assert line['impl'] == 'reference' and line['gpu_launches'] == 0
